@@ -1,0 +1,575 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE ONLY (ctypes bindings for the checker libraries).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+The product package (amatsukaze_b200) never does.
+
+Two libraries:
+  * oracle/_build/libamtk_oracle.so -- this repo's plain-C restatement (oracle/amtk_oracle.c)
+  * oracle/_ref/libamtk_ref.so      -- the reference's OWN code compiled from /root/reference by
+                                       oracle/build_ref.sh (present only where it was built; travels to the GPU box)
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "libamtk_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libamtk_ref.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_u8_p = C.POINTER(C.c_uint8)
+c_u16_p = C.POINTER(C.c_uint16)
+c_i32_p = C.POINTER(C.c_int32)
+c_f64_p = C.POINTER(C.c_double)
+
+
+def build_oracle(force=False):
+    """Compile oracle/amtk_oracle.c (gcc, no contraction, no fast-math)."""
+    src = os.path.join(HERE, "amtk_oracle.c")
+    hdr = os.path.join(HERE, "amtk_oracle.h")
+    if (not force and os.path.exists(ORACLE_SO)
+            and os.path.getmtime(ORACLE_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return ORACLE_SO
+    os.makedirs(os.path.dirname(ORACLE_SO), exist_ok=True)
+    cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
+           "-o", ORACLE_SO, src, "-lm"]
+    subprocess.check_call(cmd)
+    return ORACLE_SO
+
+
+def build_ref():
+    """Run oracle/build_ref.sh when the reference tree is present (this container only)."""
+    if os.path.exists("/root/reference/Amatsukaze/ComputeKernel.cpp"):
+        subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
+    return REF_SO if os.path.exists(REF_SO) else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class _OrLogoStruct(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("logUVx", C.c_int), ("logUVy", C.c_int),
+                ("imgw", C.c_int), ("imgh", C.c_int), ("imgx", C.c_int), ("imgy", C.c_int),
+                ("data", c_float_p), ("aY", c_float_p), ("bY", c_float_p), ("aU", c_float_p), ("bU", c_float_p),
+                ("aV", c_float_p), ("bV", c_float_p),
+                ("mask", c_u8_p), ("maskpixels", C.c_int), ("count", C.c_int),
+                ("kernels", c_float_p), ("scales", c_float_p), ("blackScore", C.c_float)]
+
+
+class _OrScanStruct(C.Structure):
+    _fields_ = [("scanw", C.c_int), ("scanh", C.c_int), ("logUVx", C.c_int), ("logUVy", C.c_int),
+                ("thy", C.c_int), ("nframes", C.c_int), ("sums", c_f64_p)]
+
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        LP = C.POINTER(_OrLogoStruct)
+        SP = C.POINTER(_OrScanStruct)
+        L.amtk_or_corr5x5.restype = C.c_float
+        L.amtk_or_corr5x5.argtypes = [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p]
+        L.amtk_or_corr5x5_scalar_order.restype = C.c_float
+        L.amtk_or_corr5x5_scalar_order.argtypes = L.amtk_or_corr5x5.argtypes
+        for n, t in (("u8", c_u8_p), ("u16", c_u16_p)):
+            for f in ("deint_y", "copy_y"):
+                fn = getattr(L, "amtk_or_%s_%s" % (f, n))
+                fn.restype = None
+                fn.argtypes = [c_float_p, t, C.c_int, C.c_int, C.c_int]
+            fn = getattr(L, "amtk_or_scan_frame_" + n)
+            fn.restype = None
+            fn.argtypes = [LP, t, C.c_int, C.c_float, c_float_p]
+            fn = getattr(L, "amtk_or_analyze_frame_" + n)
+            fn.restype = None
+            fn.argtypes = [LP, LP, LP, t, C.c_int, C.c_float, c_float_p]
+            fn = getattr(L, "amtk_or_delogo_" + n)
+            fn.restype = None
+            fn.argtypes = [t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, c_float_p, C.c_float]
+            fn = getattr(L, "amtk_or_comb_frame_" + n)
+            fn.restype = None
+            fn.argtypes = [t] * 6 + [C.c_int] * 6 + [c_i32_p, c_i32_p]
+        L.amtk_or_logo_new.restype = LP
+        L.amtk_or_logo_new.argtypes = [C.c_int] * 8 + [c_float_p]
+        L.amtk_or_logo_free.restype = None
+        L.amtk_or_logo_free.argtypes = [LP]
+        L.amtk_or_logo_deint.restype = LP
+        L.amtk_or_logo_deint.argtypes = [LP]
+        L.amtk_or_logo_field.restype = LP
+        L.amtk_or_logo_field.argtypes = [LP, C.c_int]
+        L.amtk_or_logo_create_mask.restype = None
+        L.amtk_or_logo_create_mask.argtypes = [LP, C.c_float]
+        L.amtk_or_logo_corr_score.restype = C.c_float
+        L.amtk_or_logo_corr_score.argtypes = [LP, c_float_p, C.c_float]
+        L.amtk_or_logo_evaluate.restype = C.c_float
+        L.amtk_or_logo_evaluate.argtypes = [LP, c_float_p, C.c_float, C.c_float, c_float_p, C.c_int]
+        L.amtk_or_erase_frame_u8.restype = None
+        L.amtk_or_erase_frame_u8.argtypes = [LP, c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.amtk_or_calc_fade2.restype = None
+        L.amtk_or_calc_fade2.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
+        L.amtk_or_scan_new.restype = SP
+        L.amtk_or_scan_new.argtypes = [C.c_int] * 5
+        L.amtk_or_scan_free.restype = None
+        L.amtk_or_scan_free.argtypes = [SP]
+        L.amtk_or_scan_add_frame_u8.restype = C.c_int
+        L.amtk_or_scan_add_frame_u8.argtypes = [SP, c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int]
+        L.amtk_or_scan_get_logo.restype = C.c_int
+        L.amtk_or_scan_get_logo.argtypes = [SP, C.c_int, C.c_int, c_float_p]
+        L.amtk_or_bench_scan_comb_u8.restype = C.c_double
+        L.amtk_or_bench_scan_comb_u8.argtypes = [LP, c_u8_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int, c_float_p, c_i32_p]
+        _oracle = L
+    return _oracle
+
+
+def logo_data_size(w, h, logUVx=1, logUVy=1):
+    return (w * h + (w >> logUVx) * (h >> logUVy) * 2) * 2
+
+
+class OracleLogo:
+    """amtk_or_logo handle (LogoDataParam restatement)."""
+
+    def __init__(self, ptr):
+        self.L = oracle_lib()
+        self.ptr = ptr
+
+    @classmethod
+    def create(cls, data, w, h, imgw, imgh, imgx, imgy, logUVx=1, logUVy=1):
+        L = oracle_lib()
+        d = _f32(data)
+        assert d.size == logo_data_size(w, h, logUVx, logUVy)
+        return cls(L.amtk_or_logo_new(w, h, logUVx, logUVy, imgw, imgh, imgx, imgy, _p(d, c_float_p)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.L.amtk_or_logo_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+    @property
+    def s(self):
+        return self.ptr.contents
+
+    def deint(self):
+        return OracleLogo(self.L.amtk_or_logo_deint(self.ptr))
+
+    def field(self, bottom):
+        return OracleLogo(self.L.amtk_or_logo_field(self.ptr, int(bottom)))
+
+    def create_mask(self, maskratio):
+        self.L.amtk_or_logo_create_mask(self.ptr, C.c_float(maskratio))
+        return self
+
+    def data(self):
+        s = self.s
+        n = logo_data_size(s.w, s.h, s.logUVx, s.logUVy)
+        return np.ctypeslib.as_array(s.data, shape=(n,)).copy()
+
+    def mask(self):
+        s = self.s
+        return np.ctypeslib.as_array(s.mask, shape=(s.h, s.w)).copy()
+
+    def kernels(self):
+        s = self.s
+        return np.ctypeslib.as_array(s.kernels, shape=(s.count, 25)).copy()
+
+    def scales(self):
+        s = self.s
+        return np.ctypeslib.as_array(s.scales, shape=(s.count, 32, 2)).copy()
+
+    def evaluate(self, src, maxv, fade, stride=-1):
+        s = self.s
+        src = _f32(src)
+        work = np.zeros(s.w * s.h + 8, np.float32)
+        return float(self.L.amtk_or_logo_evaluate(self.ptr, _p(src, c_float_p), C.c_float(maxv), C.c_float(fade),
+                                                  _p(work, c_float_p), stride))
+
+    def scan_frame(self, planeY, pitch=None, maxv=None):
+        a = np.ascontiguousarray(planeY)
+        pitch = a.shape[1] if pitch is None else pitch
+        out = np.zeros(2, np.float32)
+        if a.dtype == np.uint8:
+            self.L.amtk_or_scan_frame_u8(self.ptr, _p(a, c_u8_p), pitch, C.c_float(255.0 if maxv is None else maxv), _p(out, c_float_p))
+        else:
+            assert a.dtype == np.uint16
+            self.L.amtk_or_scan_frame_u16(self.ptr, _p(a, c_u16_p), pitch, C.c_float(1023.0 if maxv is None else maxv), _p(out, c_float_p))
+        return out
+
+
+def or_analyze_frame(dl, ft, fb, planeY, maxv=None, pitch=None):
+    L = oracle_lib()
+    a = np.ascontiguousarray(planeY)
+    pitch = a.shape[1] if pitch is None else pitch
+    out = np.zeros(33, np.float32)
+    if a.dtype == np.uint8:
+        L.amtk_or_analyze_frame_u8(dl.ptr, ft.ptr, fb.ptr, _p(a, c_u8_p), pitch, C.c_float(255.0 if maxv is None else maxv), _p(out, c_float_p))
+    else:
+        L.amtk_or_analyze_frame_u16(dl.ptr, ft.ptr, fb.ptr, _p(a, c_u16_p), pitch, C.c_float(1023.0 if maxv is None else maxv), _p(out, c_float_p))
+    return out
+
+
+def or_comb_frame(cur, prev, th6):
+    """cur/prev = (Y,U,V) arrays (2-D, contiguous rows = pitch).  Returns int32[12]."""
+    L = oracle_lib()
+    cy, cu, cv = [np.ascontiguousarray(p) for p in cur]
+    py, pu, pv = [np.ascontiguousarray(p) for p in prev]
+    h, w = cy.shape
+    logx = 0 if cu.shape[1] == w else 1
+    logy = 0 if cu.shape[0] == h else 1
+    th = np.asarray(th6, np.int32)
+    out = np.zeros(12, np.int32)
+    if cy.dtype == np.uint8:
+        t = c_u8_p
+        fn = L.amtk_or_comb_frame_u8
+    else:
+        t = c_u16_p
+        fn = L.amtk_or_comb_frame_u16
+    fn(_p(cy, t), _p(cu, t), _p(cv, t), _p(py, t), _p(pu, t), _p(pv, t), w, h, cy.shape[1], cu.shape[1], logx, logy,
+       _p(th, c_i32_p), _p(out, c_i32_p))
+    return out
+
+
+def or_comb_clip(Y, U, V, th6):
+    """Y:(N,H,W) U,V:(N,H/2,W/2) -> int32 (N,12) with prev(0)=frame 0."""
+    n = Y.shape[0]
+    out = np.zeros((n, 12), np.int32)
+    for i in range(n):
+        j = max(i - 1, 0)
+        out[i] = or_comb_frame((Y[i], U[i], V[i]), (Y[j], U[j], V[j]), th6)
+    return out
+
+
+def or_delogo(dst, A, B, fade, maxv, logopitch=None, imgpitch=None, w=None, h=None):
+    L = oracle_lib()
+    a = dst
+    assert a.flags["C_CONTIGUOUS"]
+    A = _f32(A)
+    B = _f32(B)
+    h = a.shape[0] if h is None else h
+    w = a.shape[1] if w is None else w
+    imgpitch = a.shape[1] if imgpitch is None else imgpitch
+    logopitch = w if logopitch is None else logopitch
+    if a.dtype == np.uint8:
+        L.amtk_or_delogo_u8(_p(a, c_u8_p), w, h, logopitch, imgpitch, C.c_float(maxv), _p(A, c_float_p), _p(B, c_float_p), C.c_float(fade))
+    else:
+        L.amtk_or_delogo_u16(_p(a, c_u16_p), w, h, logopitch, imgpitch, C.c_float(maxv), _p(A, c_float_p), _p(B, c_float_p), C.c_float(fade))
+    return a
+
+
+def or_erase_frame(logo, Y, U, V, fadeT, fadeB, maxv=255.0):
+    L = oracle_lib()
+    for p in (Y, U, V):
+        assert p.flags["C_CONTIGUOUS"] and p.dtype == np.uint8
+    L.amtk_or_erase_frame_u8(logo.ptr, _p(Y, c_u8_p), _p(U, c_u8_p), _p(V, c_u8_p), Y.shape[1], U.shape[1],
+                             C.c_float(maxv), C.c_float(fadeT), C.c_float(fadeB))
+
+
+def or_calc_fade2(records, num_frames, n):
+    L = oracle_lib()
+    r = _f32(records).reshape(-1, 33)
+    ft = C.c_float()
+    fb = C.c_float()
+    L.amtk_or_calc_fade2(_p(r, c_float_p), r.shape[0], num_frames, n, C.byref(ft), C.byref(fb))
+    return ft.value, fb.value
+
+
+class OracleScan:
+    def __init__(self, scanw, scanh, thy, logUVx=1, logUVy=1):
+        self.L = oracle_lib()
+        self.ptr = self.L.amtk_or_scan_new(scanw, scanh, logUVx, logUVy, thy)
+        self.ny = scanw * scanh
+        self.nc = (scanw >> logUVx) * (scanh >> logUVy)
+        self.n = logo_data_size(scanw, scanh, logUVx, logUVy)
+
+    def __del__(self):
+        try:
+            self.L.amtk_or_scan_free(self.ptr)
+        except Exception:
+            pass
+
+    def add_frame(self, y, u, v, pitchY=None, pitchUV=None):
+        y, u, v = [np.ascontiguousarray(p, np.uint8) for p in (y, u, v)]
+        return self.L.amtk_or_scan_add_frame_u8(self.ptr, _p(y, c_u8_p), _p(u, c_u8_p), _p(v, c_u8_p),
+                                                y.shape[1] if pitchY is None else pitchY,
+                                                u.shape[1] if pitchUV is None else pitchUV)
+
+    @property
+    def nframes(self):
+        return self.ptr.contents.nframes
+
+    def sums(self):
+        return np.ctypeslib.as_array(self.ptr.contents.sums, shape=(self.ny + 2 * self.nc, 5)).copy()
+
+    def set_sums(self, sums, nframes):
+        s = np.ascontiguousarray(sums, np.float64).reshape(-1)
+        C.memmove(self.ptr.contents.sums, s.ctypes.data, s.nbytes)
+        self.ptr.contents.nframes = nframes
+
+    def get_logo(self, maxv=255, clean=False):
+        out = np.zeros(self.n, np.float32)
+        ok = self.L.amtk_or_scan_get_logo(self.ptr, maxv, int(clean), _p(out, c_float_p))
+        return out if ok else None
+
+
+# ----------------------------------------------------------------------------------------------------
+# The reference's own code (oracle/_ref/libamtk_ref.so)
+# ----------------------------------------------------------------------------------------------------
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            raise RuntimeError("oracle/_ref/libamtk_ref.so missing: run oracle/build_ref.sh where /root/reference exists")
+        R = C.CDLL(REF_SO)
+        V = C.c_void_p
+        R.ref_corr5x5_avx.restype = C.c_float
+        R.ref_corr5x5_avx.argtypes = [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p]
+        R.ref_corr5x5_scalar.restype = C.c_float
+        R.ref_corr5x5_scalar.argtypes = R.ref_corr5x5_avx.argtypes
+        R.ref_is_avx.restype = C.c_int
+        R.ref_logo_create.restype = V
+        R.ref_logo_create.argtypes = [C.c_int] * 8 + [c_float_p]
+        R.ref_logo_free.argtypes = [V]
+        R.ref_logo_deint.restype = V
+        R.ref_logo_deint.argtypes = [V]
+        R.ref_logo_field.restype = V
+        R.ref_logo_field.argtypes = [V, C.c_int]
+        R.ref_logo_create_mask.argtypes = [V, C.c_float]
+        R.ref_logo_dims.argtypes = [V, C.POINTER(C.c_int)]
+        R.ref_logo_get_data.argtypes = [V, c_float_p]
+        R.ref_logo_black_score.restype = C.c_float
+        R.ref_logo_black_score.argtypes = [V]
+        R.ref_logo_get_mask.argtypes = [V, c_u8_p]
+        R.ref_logo_get_kernels.argtypes = [V, c_float_p, C.c_int]
+        R.ref_logo_get_scales.argtypes = [V, c_float_p, C.c_int]
+        R.ref_logo_evaluate.restype = C.c_float
+        R.ref_logo_evaluate.argtypes = [V, c_float_p, C.c_float, C.c_float, c_float_p, C.c_int]
+        R.ref_logo_corr_score.restype = C.c_float
+        R.ref_logo_corr_score.argtypes = [V, c_float_p, C.c_float]
+        R.ref_logo_save.restype = C.c_int
+        R.ref_logo_save.argtypes = [V, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        R.ref_logo_load.restype = V
+        R.ref_logo_load.argtypes = [C.c_char_p, C.c_void_p]
+        R.ref_sizeof.restype = C.c_int
+        R.ref_sizeof.argtypes = [C.c_int]
+        for n, t in (("u8", c_u8_p), ("u16", c_u16_p)):
+            for f in ("deint_y", "copy_y"):
+                fn = getattr(R, "ref_%s_%s" % (f, n))
+                fn.restype = None
+                fn.argtypes = [c_float_p, t, C.c_int, C.c_int, C.c_int]
+            fn = getattr(R, "ref_scan_add_frame_" + n)
+            fn.restype = C.c_int
+            fn.argtypes = [V, t, t, t, C.c_int, C.c_int]
+        R.ref_scan_create.restype = V
+        R.ref_scan_create.argtypes = [C.c_int] * 5
+        R.ref_scan_free.argtypes = [V]
+        R.ref_scan_nframes.restype = C.c_int
+        R.ref_scan_nframes.argtypes = [V]
+        R.ref_scan_get_sums.argtypes = [V, c_f64_p]
+        R.ref_scan_set_sums.argtypes = [V, c_f64_p, C.c_int]
+        R.ref_scan_normalize.argtypes = [V, C.c_int]
+        R.ref_scan_get_logo.restype = C.c_int
+        R.ref_scan_get_logo.argtypes = [V, C.c_int, c_float_p]
+        _ref = R
+    return _ref
+
+
+class RefLogo:
+    """The reference's LogoDataParam (compiled from /root/reference)."""
+
+    def __init__(self, ptr):
+        self.R = ref_lib()
+        self.ptr = C.c_void_p(ptr)
+
+    @classmethod
+    def create(cls, data, w, h, imgw, imgh, imgx, imgy, logUVx=1, logUVy=1):
+        R = ref_lib()
+        d = _f32(data)
+        assert d.size == logo_data_size(w, h, logUVx, logUVy)
+        return cls(R.ref_logo_create(w, h, logUVx, logUVy, imgw, imgh, imgx, imgy, _p(d, c_float_p)))
+
+    @classmethod
+    def load(cls, path):
+        R = ref_lib()
+        hdr = np.zeros(540, np.uint8)
+        p = R.ref_logo_load(path.encode(), hdr.ctypes.data_as(C.c_void_p))
+        if not p:
+            return None, None
+        return cls(p), hdr
+
+    def save(self, path, imgw, imgh, imgx, imgy, name="No Name", service_id=0):
+        return self.R.ref_logo_save(self.ptr, path.encode(), imgw, imgh, imgx, imgy, name.encode(), service_id)
+
+    def __del__(self):
+        try:
+            self.R.ref_logo_free(self.ptr)
+        except Exception:
+            pass
+
+    def dims(self):
+        v = (C.c_int * 10)()
+        self.R.ref_logo_dims(self.ptr, v)
+        return dict(zip(("w", "h", "logUVx", "logUVy", "imgw", "imgh", "imgx", "imgy", "maskpixels"), list(v)[:9]))
+
+    def deint(self):
+        return RefLogo(self.R.ref_logo_deint(self.ptr))
+
+    def field(self, bottom):
+        return RefLogo(self.R.ref_logo_field(self.ptr, int(bottom)))
+
+    def create_mask(self, maskratio):
+        self.R.ref_logo_create_mask(self.ptr, C.c_float(maskratio))
+        return self
+
+    def data(self):
+        d = self.dims()
+        out = np.zeros(logo_data_size(d["w"], d["h"], d["logUVx"], d["logUVy"]), np.float32)
+        self.R.ref_logo_get_data(self.ptr, _p(out, c_float_p))
+        return out
+
+    def black_score(self):
+        return float(self.R.ref_logo_black_score(self.ptr))
+
+    def mask(self):
+        d = self.dims()
+        out = np.zeros((d["h"], d["w"]), np.uint8)
+        self.R.ref_logo_get_mask(self.ptr, _p(out, c_u8_p))
+        return out
+
+    def visited_count(self):
+        m = self.mask()
+        return int(m[2:-2, 2:-2].sum())
+
+    def kernels(self):
+        n = self.visited_count()
+        out = np.zeros((n, 25), np.float32)
+        self.R.ref_logo_get_kernels(self.ptr, _p(out, c_float_p), n)
+        return out
+
+    def scales(self):
+        n = self.visited_count()
+        out = np.zeros((n, 32, 2), np.float32)
+        self.R.ref_logo_get_scales(self.ptr, _p(out, c_float_p), n)
+        return out
+
+    def evaluate(self, src, maxv, fade, stride=-1):
+        d = self.dims()
+        src = _f32(src)
+        work = np.zeros(d["w"] * d["h"] + 8, np.float32)
+        return float(self.R.ref_logo_evaluate(self.ptr, _p(src, c_float_p), C.c_float(maxv), C.c_float(fade),
+                                              _p(work, c_float_p), stride))
+
+
+def ref_deint_y(plane, w, h, off=0, pitch=None):
+    R = ref_lib()
+    a = np.ascontiguousarray(plane)
+    pitch = a.shape[1] if pitch is None else pitch
+    out = np.zeros(w * h + 8, np.float32)
+    flat = a.reshape(-1)[off:]
+    if a.dtype == np.uint8:
+        R.ref_deint_y_u8(_p(out, c_float_p), flat.ctypes.data_as(c_u8_p), pitch, w, h)
+    else:
+        R.ref_deint_y_u16(_p(out, c_float_p), flat.ctypes.data_as(c_u16_p), pitch, w, h)
+    return out
+
+
+def ref_copy_y(plane, w, h, off=0, pitch=None):
+    R = ref_lib()
+    a = np.ascontiguousarray(plane)
+    pitch = a.shape[1] if pitch is None else pitch
+    out = np.zeros(w * h + 8, np.float32)
+    flat = a.reshape(-1)[off:]
+    if a.dtype == np.uint8:
+        R.ref_copy_y_u8(_p(out, c_float_p), flat.ctypes.data_as(c_u8_p), pitch, w, h)
+    else:
+        R.ref_copy_y_u16(_p(out, c_float_p), flat.ctypes.data_as(c_u16_p), pitch, w, h)
+    return out
+
+
+def ref_scan_frame(deint_logo, planeY, maxv=None, pitch=None):
+    """LogoFrame::ScanFrame (LogoScan.hpp:1559-1566) composed from the reference's own DeintY + EvaluateLogo."""
+    d = deint_logo.dims()
+    a = np.ascontiguousarray(planeY)
+    pitch = a.shape[1] if pitch is None else pitch
+    maxv = (255.0 if a.dtype == np.uint8 else 1023.0) if maxv is None else maxv
+    de = ref_deint_y(a, d["w"], d["h"], off=d["imgx"] + d["imgy"] * pitch, pitch=pitch)
+    return np.array([deint_logo.evaluate(de, maxv, 0.0), deint_logo.evaluate(de, maxv, 1.0)], np.float32)
+
+
+def ref_analyze_frame(dl, ft, fb, planeY, maxv=None, pitch=None):
+    """AMTAnalyzeLogo::GetFrameT per source frame (LogoScan.hpp:1146-1155) from the reference's own pieces."""
+    d = dl.dims()
+    a = np.ascontiguousarray(planeY)
+    pitch = a.shape[1] if pitch is None else pitch
+    maxv = (255.0 if a.dtype == np.uint8 else 1023.0) if maxv is None else maxv
+    off = d["imgx"] + d["imgy"] * pitch
+    w, h = d["w"], d["h"]
+    cp = ref_copy_y(a, w, h, off=off, pitch=pitch)
+    de = ref_deint_y(a, w, h, off=off, pitch=pitch)
+    out = np.zeros(33, np.float32)
+    for f in range(11):
+        fade = np.float32(f) / np.float32(10.0)
+        out[f] = abs(np.float32(dl.evaluate(de, maxv, fade)))
+        out[11 + f] = abs(np.float32(ft.evaluate(cp, maxv, fade, stride=2 * w)))
+        out[22 + f] = abs(np.float32(fb.evaluate(cp[w:], maxv, fade, stride=2 * w)))
+    return out
+
+
+class RefScan:
+    def __init__(self, scanw, scanh, thy, logUVx=1, logUVy=1):
+        self.R = ref_lib()
+        self.ptr = C.c_void_p(self.R.ref_scan_create(scanw, scanh, logUVx, logUVy, thy))
+        self.ny = scanw * scanh
+        self.nc = (scanw >> logUVx) * (scanh >> logUVy)
+        self.n = logo_data_size(scanw, scanh, logUVx, logUVy)
+
+    def __del__(self):
+        try:
+            self.R.ref_scan_free(self.ptr)
+        except Exception:
+            pass
+
+    def add_frame(self, y, u, v, pitchY=None, pitchUV=None):
+        y, u, v = [np.ascontiguousarray(p, np.uint8) for p in (y, u, v)]
+        return self.R.ref_scan_add_frame_u8(self.ptr, _p(y, c_u8_p), _p(u, c_u8_p), _p(v, c_u8_p),
+                                            y.shape[1] if pitchY is None else pitchY,
+                                            u.shape[1] if pitchUV is None else pitchUV)
+
+    @property
+    def nframes(self):
+        return self.R.ref_scan_nframes(self.ptr)
+
+    def sums(self):
+        out = np.zeros((self.ny + 2 * self.nc, 5), np.float64)
+        self.R.ref_scan_get_sums(self.ptr, _p(out, c_f64_p))
+        return out
+
+    def set_sums(self, sums, nframes):
+        s = np.ascontiguousarray(sums, np.float64)
+        self.R.ref_scan_set_sums(self.ptr, _p(s, c_f64_p), nframes)
+
+    def get_logo(self, maxv=255, clean=False):
+        """Normalize(maxv) then GetLogo(clean) on a COPY of the accumulators (Normalize is destructive)."""
+        saved = self.sums()
+        n = self.nframes
+        self.R.ref_scan_normalize(self.ptr, maxv)
+        out = np.zeros(self.n, np.float32)
+        ok = self.R.ref_scan_get_logo(self.ptr, int(clean), _p(out, c_float_p))
+        self.set_sums(saved, n)
+        return out if ok else None

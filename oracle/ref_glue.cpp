@@ -1,0 +1,146 @@
+/* oracle/ref_glue.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+ *
+ * extern "C" handles around the reference's own classes, which build_ref.sh extracts VERBATIM by line
+ * range from /root/reference into oracle/_ref/ref_extract.inc (git-ignored, never committed):
+ *   AMTLogo.hpp:17-282      LogoHeader, LogoData (+ .lgd Save/Load)
+ *   LogoScan.hpp:24-45      scalar CalcCorrelation5x5 + decl of the AVX one (ComputeKernel.cpp:77-121)
+ *   LogoScan.hpp:59-660     LogoDataParam, approxim_line, LogoColor, LogoScan
+ *   LogoScan.hpp:734-790    DeintLogo, DeintY, CopyY
+ * This file adds no arithmetic of its own: every function forwards to the extracted code.
+ * `private`/`protected` are opened (oracle build only) so the tests can read the tables the reference
+ * keeps private (scales, blackScore, LogoColor sums) -- SURVEY.md Appendix A item 4. */
+#include "ref_shim.h"
+#define private public
+#define protected public
+#define class struct   /* members before the first access specifier are private in the reference's classes */
+#include "ref_extract.inc"
+#undef class
+#undef private
+#undef protected
+
+using namespace logo;
+
+extern "C" {
+
+/* ---- ComputeKernel.cpp / LogoScan.hpp:24-41 ---- */
+float ref_corr5x5_avx(const float* k, const float* Y, int x, int y, int w, float* pavg) {
+  return CalcCorrelation5x5_AVX(k, Y, x, y, w, pavg);
+}
+float ref_corr5x5_scalar(const float* k, const float* Y, int x, int y, int w, float* pavg) {
+  return CalcCorrelation5x5(k, Y, x, y, w, pavg);
+}
+int ref_is_avx(void) { return IsAVXAvailable() ? 1 : 0; }
+
+/* ---- LogoDataParam ---- */
+/* data = aY,bY,aU,bU,aV,bV contiguous, exactly LogoData's own layout (AMTLogo.hpp:206-212) */
+void* ref_logo_create(int w, int h, int logUVx, int logUVy, int imgw, int imgh, int imgx, int imgy, const float* data) {
+  LogoData d(w, h, logUVx, logUVy);
+  size_t n = (size_t)(w * h + (w >> logUVx) * (h >> logUVy) * 2) * 2;
+  memcpy(d.data.get(), data, n * sizeof(float));
+  return new LogoDataParam(std::move(d), imgw, imgh, imgx, imgy);
+}
+void ref_logo_free(void* p) { delete (LogoDataParam*)p; }
+/* LogoFrame ctor / AMTAnalyzeLogo ctor: deint logo built from a loaded logo (LogoScan.hpp:1605-1607,1177-1179) */
+void* ref_logo_deint(void* src) {
+  LogoDataParam* s = (LogoDataParam*)src;
+  LogoDataParam* d = new LogoDataParam(LogoData(s->w, s->h, s->logUVx, s->logUVy), s->imgw, s->imgh, s->imgx, s->imgy);
+  DeintLogo(*d, *s, s->w, s->h);
+  return d;
+}
+void* ref_logo_field(void* src, int bottom) { return ((LogoDataParam*)src)->MakeFieldLogo(bottom != 0).release(); }
+void ref_logo_create_mask(void* p, float maskratio) { ((LogoDataParam*)p)->CreateLogoMask(maskratio); }
+void ref_logo_dims(void* p, int* out10) {
+  LogoDataParam* s = (LogoDataParam*)p;
+  int v[10] = { s->w, s->h, s->logUVx, s->logUVy, s->imgw, s->imgh, s->imgx, s->imgy, s->maskpixels, 0 };
+  memcpy(out10, v, sizeof(v));
+}
+void ref_logo_get_data(void* p, float* out) {
+  LogoDataParam* s = (LogoDataParam*)p;
+  size_t n = (size_t)(s->w * s->h + (s->w >> s->logUVx) * (s->h >> s->logUVy) * 2) * 2;
+  memcpy(out, s->data.get(), n * sizeof(float));
+}
+float ref_logo_black_score(void* p) { return ((LogoDataParam*)p)->blackScore; }
+void ref_logo_get_mask(void* p, uint8_t* out) { LogoDataParam* s = (LogoDataParam*)p; memcpy(out, s->mask.get(), (size_t)s->w * s->h); }
+/* only the first `count` (visited) entries are initialised by the reference (LogoScan.hpp:186-200) */
+void ref_logo_get_kernels(void* p, float* out, int count) { memcpy(out, ((LogoDataParam*)p)->kernels.get(), (size_t)count * 25 * sizeof(float)); }
+void ref_logo_get_scales(void* p, float* out, int count) { memcpy(out, ((LogoDataParam*)p)->scales.get(), (size_t)count * 32 * 2 * sizeof(float)); }
+float ref_logo_evaluate(void* p, const float* src, float maxv, float fade, float* work, int stride) {
+  return ((LogoDataParam*)p)->EvaluateLogo(src, maxv, fade, work, stride);
+}
+float ref_logo_corr_score(void* p, const float* work, float maxv) { return ((LogoDataParam*)p)->CorrelationScore(work, maxv); }
+
+/* ---- .lgd I/O (AMTLogo.hpp:239-279) ---- */
+int ref_logo_save(void* p, const char* path, int imgw, int imgh, int imgx, int imgy, const char* name, int serviceId) {
+  LogoDataParam* s = (LogoDataParam*)p;
+  try {
+    LogoHeader hd(s->w, s->h, s->logUVx, s->logUVy, imgw, imgh, imgx, imgy, name);
+    hd.serviceId = serviceId;
+    s->Save(path, &hd);
+    return 1;
+  } catch (const IOException&) { return 0; }
+}
+void* ref_logo_load(const char* path, void* header540) {
+  try {
+    LogoHeader hd;
+    LogoData d = LogoData::Load(path, &hd);
+    if (header540) memcpy(header540, &hd, sizeof(hd));
+    return new LogoDataParam(std::move(d), &hd);
+  } catch (const IOException&) { return nullptr; }
+}
+int ref_sizeof(int which) {
+  switch (which) { case 0: return (int)sizeof(LogoHeader); case 1: return (int)sizeof(LOGO_FILE_HEADER);
+                   case 2: return (int)sizeof(LOGO_HEADER); case 3: return (int)sizeof(LOGO_PIXEL); }
+  return -1;
+}
+
+/* ---- DeintY / CopyY (LogoScan.hpp:763-790) ---- */
+void ref_deint_y_u8(float* dst, const uint8_t* src, int pitch, int w, int h) { DeintY<uint8_t>(dst, src, pitch, w, h); }
+void ref_deint_y_u16(float* dst, const uint16_t* src, int pitch, int w, int h) { DeintY<uint16_t>(dst, src, pitch, w, h); }
+void ref_copy_y_u8(float* dst, const uint8_t* src, int pitch, int w, int h) { CopyY<uint8_t>(dst, src, pitch, w, h); }
+void ref_copy_y_u16(float* dst, const uint16_t* src, int pitch, int w, int h) { CopyY<uint16_t>(dst, src, pitch, w, h); }
+
+/* ---- LogoScan (LogoScan.hpp:398-660) ---- */
+void* ref_scan_create(int scanw, int scanh, int logUVx, int logUVy, int thy) { return new LogoScan(scanw, scanh, logUVx, logUVy, thy); }
+void ref_scan_free(void* p) { delete (LogoScan*)p; }
+int ref_scan_add_frame_u8(void* p, const uint8_t* y, const uint8_t* u, const uint8_t* v, int pitchY, int pitchUV) {
+  return ((LogoScan*)p)->AddFrame<uint8_t>(y, u, v, pitchY, pitchUV) ? 1 : 0;
+}
+int ref_scan_add_frame_u16(void* p, const uint16_t* y, const uint16_t* u, const uint16_t* v, int pitchY, int pitchUV) {
+  return ((LogoScan*)p)->AddFrame<uint16_t>(y, u, v, pitchY, pitchUV) ? 1 : 0;
+}
+int ref_scan_nframes(void* p) { return ((LogoScan*)p)->nframes; }
+/* raw accumulators, plane-major (Y then U then V), 5 doubles per pixel: sumF,sumB,sumF2,sumB2,sumFB */
+void ref_scan_get_sums(void* p, double* out) {
+  LogoScan* s = (LogoScan*)p;
+  int ny = s->scanw * s->scanh, nc = ny >> (s->logUVx + s->logUVy);
+  const LogoColor* planes[3] = { s->logoY.get(), s->logoU.get(), s->logoV.get() };
+  int cnt[3] = { ny, nc, nc };
+  for (int pl = 0; pl < 3; ++pl) for (int i = 0; i < cnt[pl]; ++i) {
+    const LogoColor& c = planes[pl][i];
+    *out++ = c.sumF; *out++ = c.sumB; *out++ = c.sumF2; *out++ = c.sumB2; *out++ = c.sumFB;
+  }
+}
+/* overwrite accumulators (lets a test finalise GPU-produced integer sums through the reference's own GetLogo) */
+void ref_scan_set_sums(void* p, const double* in, int nframes) {
+  LogoScan* s = (LogoScan*)p;
+  int ny = s->scanw * s->scanh, nc = ny >> (s->logUVx + s->logUVy);
+  LogoColor* planes[3] = { s->logoY.get(), s->logoU.get(), s->logoV.get() };
+  int cnt[3] = { ny, nc, nc };
+  for (int pl = 0; pl < 3; ++pl) for (int i = 0; i < cnt[pl]; ++i) {
+    LogoColor& c = planes[pl][i];
+    c.sumF = *in++; c.sumB = *in++; c.sumF2 = *in++; c.sumB2 = *in++; c.sumFB = *in++;
+  }
+  s->nframes = nframes;
+}
+void ref_scan_normalize(void* p, int maxv) { ((LogoScan*)p)->Normalize(maxv); }
+/* returns 1 and fills out (LogoData layout) or 0 when the reference returns nullptr (LogoScan.hpp:503,508-509) */
+int ref_scan_get_logo(void* p, int clean, float* out) {
+  LogoScan* s = (LogoScan*)p;
+  std::unique_ptr<LogoData> d = s->GetLogo(clean != 0);
+  if (!d) return 0;
+  size_t n = (size_t)(s->scanw * s->scanh + (s->scanw >> s->logUVx) * (s->scanh >> s->logUVy) * 2) * 2;
+  memcpy(out, d->data.get(), n * sizeof(float));
+  return 1;
+}
+
+} /* extern "C" */
