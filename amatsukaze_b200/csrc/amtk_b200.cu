@@ -1,0 +1,770 @@
+// amtk_b200.cu -- the C ABI of libamtk_b200.so (include/amtk_b200.h) and all kernel launches.
+// Host side of the drop-in boundary: validates arguments, moves host-resident clips through HBM staging buffers,
+// builds TMA descriptors and the static work partition, launches the sm_100a kernels.  No CPU compute fallback.
+#include "amtk_internal.h"
+#include "logo_kernels.cuh"
+#include "comb_kernels.cuh"
+#include "scan_kernels.cuh"
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+extern "C" { static int logo_ensure_device(const amtk_logo* cl, amtk_ctx* ctx, bool need_tables); }
+
+namespace amtk {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+  return false;
+}
+
+LogoDev logo_dev(const amtk_logo* l) {
+  LogoDev d;
+  d.w = l->host.w; d.h = l->host.h; d.count = l->host.count(); d.countPad = l->countPad;
+  d.blackScore = l->host.blackScore; d.A = l->dA; d.B = l->dB; d.pix = l->dPix; d.tapsT = l->dTapsT; d.scales = l->dScales;
+  return d;
+}
+
+static bool ensure(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return true;
+  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+  size_t sz = std::max(need, (size_t)1 << 20);
+  if (!cuda_ok(cudaMalloc(p, sz), "cudaMalloc(scratch)")) return false;
+  *cap = sz;
+  return true;
+}
+
+struct DevSelect {   // RAII: make the context's device current for the duration of a call
+  int prev = -1; bool ok = true;
+  explicit DevSelect(const amtk_ctx* c) { ok = cuda_ok(cudaGetDevice(&prev), "cudaGetDevice") && cuda_ok(cudaSetDevice(c->device), "cudaSetDevice"); }
+  ~DevSelect() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static bool validate_clip(const amtk_clip* c, bool need_chroma) {
+  if (!c || !c->base) { set_error("clip: null"); return false; }
+  if (c->bytes_per_sample != 1 && c->bytes_per_sample != 2) { set_error("Unsupported pixel format"); return false; }
+  if (c->width <= 0 || c->height <= 0 || c->num_frames <= 0) { set_error("clip: bad geometry"); return false; }
+  if (c->pitch_y < c->width * c->bytes_per_sample) { set_error("clip: pitch_y smaller than a row"); return false; }
+  if (need_chroma && c->pitch_uv < (c->width >> c->log_uvx) * c->bytes_per_sample) { set_error("clip: pitch_uv smaller than a row"); return false; }
+  return true;
+}
+
+// A device-resident window of a clip: frames [first, first+count) of the clip are at dev_base + i*frame_stride
+// (i = frame - first).
+struct Window { const uint8_t* dev_base; int first; int count; };
+
+// Runs fn(window, lo, hi) so that frames [lo,hi) (clip numbering) are resident; with need_prev the frame lo-1 is
+// resident too when lo > 0.  Device clips: one call, zero copies.  Host clips: double-buffered H2D staging on the
+// copy stream, overlapped with the kernels of the previous chunk.
+template <typename Fn>
+static int for_each_window(amtk_ctx* ctx, const amtk_clip* clip, int frame0, int nframes, bool need_prev, Fn fn) {
+  if (frame0 < 0 || nframes < 0 || frame0 + nframes > clip->num_frames) AMTK_FAIL("frame range outside the clip");
+  if (nframes == 0) return 1;
+  if (clip->on_device) {
+    Window w{ reinterpret_cast<const uint8_t*>(clip->base), 0, clip->num_frames };
+    return fn(w, frame0, frame0 + nframes);
+  }
+  const size_t fs = (size_t)clip->frame_stride;
+  const size_t budget = (size_t)256 << 20;
+  int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)nframes, budget / fs));
+  if (need_prev && per > 1) per -= 1;
+  const size_t need = (size_t)(per + (need_prev ? 1 : 0)) * fs;
+  if (ctx->stage_bytes < need) {
+    for (int b = 0; b < 2; ++b) { if (ctx->stage[b]) cudaFree(ctx->stage[b]); ctx->stage[b] = nullptr; }
+    ctx->stage_bytes = 0;
+    for (int b = 0; b < 2; ++b) AMTK_CUDA(cudaMalloc(&ctx->stage[b], need));
+    ctx->stage_bytes = need;
+  }
+  int chunk = 0;
+  for (int lo = frame0; lo < frame0 + nframes; lo += per, ++chunk) {
+    const int hi = std::min(frame0 + nframes, lo + per);
+    const int b = chunk & 1;
+    const int first = (need_prev && lo > 0) ? lo - 1 : lo;
+    AMTK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));      // previous user of this buffer
+    AMTK_CUDA(cudaMemcpyAsync(ctx->stage[b], reinterpret_cast<const uint8_t*>(clip->base) + (size_t)first * fs,
+                              (size_t)(hi - first) * fs, cudaMemcpyHostToDevice, ctx->copy_stream));
+    AMTK_CUDA(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+    AMTK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+    Window w{ reinterpret_cast<const uint8_t*>(ctx->stage[b]), first, hi - first };
+    if (!fn(w, lo, hi)) return 0;
+    AMTK_CUDA(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+  }
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// logo evaluation launches
+// ---------------------------------------------------------------------------------------------------------
+struct EvalSpec {
+  const amtk_logo* logo;      // evaluated logo (mask built)
+  int roi_x, roi_y;           // staged rectangle (the FULL logo rectangle, frame coordinates)
+  int roi_w, roi_h;
+  int src_mode, src_off, src_stride;
+  int nfades; const float* fades;
+  int take_abs;
+  int out_off, out_fade_stride;     // where in an output row the values go
+};
+
+static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi, int pitch_elems,
+                       const EvalSpec& sp, float* dout, int out_frame_stride, int out_row0) {
+  const amtk::HostLogo& hl = sp.logo->host;
+  if (!logo_ensure_device(sp.logo, ctx, true)) return 0;
+  if (sp.nfades < 1 || sp.nfades > kMaxFades) AMTK_FAIL("too many fade levels");
+  const int count = hl.count();
+  const int bits = clip->bits_per_sample;
+  const float maxv = (float)((1 << bits) - 1);
+  if (count == 0) {   // degenerate logo: CorrelationScore is 0 -> 0/blackScore
+    AMTK_FAIL("logo has no feature pixels");
+  }
+  const int countPad = sp.logo->countPad;
+  const size_t smem = ((size_t)((sp.roi_w * sp.roi_h + 3) & ~3) + (size_t)hl.w * hl.h + 8) * sizeof(float);
+  if (smem > 200 * 1024) AMTK_FAIL("logo too large for the shared-memory evaluation path");
+  // frames per launch bounded by the score scratch (<= 96 MB)
+  const size_t per_frame = (size_t)sp.nfades * countPad * sizeof(float);
+  const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)(hi - lo), ((size_t)96 << 20) / per_frame));
+  if (!ensure(&ctx->scratch, &ctx->scratch_bytes, per_frame * batch)) return 0;
+  for (int f0 = lo; f0 < hi; f0 += batch) {
+    const int n = std::min(batch, hi - f0);
+    EvalJob job;
+    job.ybase = win.dev_base; job.frame_stride = clip->frame_stride; job.pitch = pitch_elems;
+    job.frame0 = f0 - win.first; job.nframes = n;
+    job.imgx = sp.roi_x; job.imgy = sp.roi_y;
+    job.roi_w = sp.roi_w; job.roi_h = sp.roi_h;
+    job.src_mode = sp.src_mode; job.src_off = sp.src_off; job.src_stride = sp.src_stride;
+    job.logo = logo_dev(sp.logo); job.maxv = maxv; job.nfades = sp.nfades;
+    for (int i = 0; i < sp.nfades; ++i) job.fades[i] = sp.fades[i];
+    job.scores = reinterpret_cast<float*>(ctx->scratch);
+    const int slices3 = (count + kEvalThreads * 3 - 1) / (kEvalThreads * 3);
+    int pxt = 3, slices = slices3;
+    if (count <= kEvalThreads) { pxt = 1; slices = 1; }
+    else if (count <= kEvalThreads * 2) { pxt = 2; slices = 1; }
+    const int lanes = std::max(1, std::min(n, (ctx->sm_count * 2) / slices));
+    dim3 grid(slices, lanes);
+    const bool u16 = clip->bytes_per_sample == 2;
+#define AMTK_LAUNCH_SCORES(T, P)                                                                              \
+  do {                                                                                                        \
+    AMTK_CUDA(cudaFuncSetAttribute(logo_scores_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    logo_scores_kernel<T, P><<<grid, kEvalThreads, smem, ctx->stream>>>(job);                                 \
+  } while (0)
+    if (!u16) { if (pxt == 1) AMTK_LAUNCH_SCORES(uint8_t, 1); else if (pxt == 2) AMTK_LAUNCH_SCORES(uint8_t, 2); else AMTK_LAUNCH_SCORES(uint8_t, 3); }
+    else      { if (pxt == 1) AMTK_LAUNCH_SCORES(uint16_t, 1); else if (pxt == 2) AMTK_LAUNCH_SCORES(uint16_t, 2); else AMTK_LAUNCH_SCORES(uint16_t, 3); }
+#undef AMTK_LAUNCH_SCORES
+    AMTK_CUDA(cudaGetLastError());
+    const int total = n * sp.nfades;
+    logo_sum_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(
+        job.scores, count, countPad, n, sp.nfades, hl.blackScore, sp.take_abs,
+        dout + (size_t)(f0 - out_row0) * out_frame_stride, out_frame_stride, sp.out_off, sp.out_fade_stride);
+    AMTK_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  return 1;
+}
+
+static bool roi_inside(const amtk::HostLogo& full, const amtk_clip* clip, int pitch_elems) {
+  // the ROI rows must lie inside the frame allocation as addressed with pitch_elems
+  if (full.imgx < 0 || full.imgy < 0) return false;
+  const long long last = (long long)full.imgx + full.w - 1 + (long long)(full.imgy + full.h - 1) * pitch_elems;
+  const long long plane_elems = (long long)clip->pitch_y / clip->bytes_per_sample * clip->height;
+  return full.imgx + full.w <= pitch_elems && last < plane_elems;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// comb launch
+// ---------------------------------------------------------------------------------------------------------
+static int comb_thresholds_ok(const amtk_comb_params* p) {
+  const int m[2] = { p->th_move_y, p->th_move_c };
+  const int s[4] = { p->th_shima_y, p->th_lshima_y, p->th_shima_c, p->th_lshima_c };
+  for (int v : m) if (v < 1 || v > 128) { set_error("comb: th_move must be in [1,128]"); return 0; }
+  for (int v : s) if (v < 1 || v > 2047) { set_error("comb: th_shima/th_lshima must be in [1,2047]"); return 0; }
+  return 1;
+}
+
+static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi,
+                       const amtk_comb_params* prm, int* dcounts, int out_row0) {
+  if (clip->bytes_per_sample != 1) AMTK_FAIL("comb: 16-bit samples are not supported by this build (YV12 only)");
+  if ((clip->frame_stride & 15) || (clip->pitch_y & 15) || (clip->pitch_uv & 15) || (clip->off_u & 15) || (clip->off_v & 15) ||
+      (reinterpret_cast<uintptr_t>(win.dev_base) & 15))
+    AMTK_FAIL("comb: base, frame_stride, plane offsets and pitches must be multiples of 16 bytes (TMA)");
+  if (!ctx->encode_tiled) AMTK_FAIL("cuTensorMapEncodeTiled unavailable (driver too old?)");
+  CombArgs args;
+  memset(&args, 0, sizeof(args));
+  int tile0 = 0;
+  for (int pl = 0; pl < 3; ++pl) {
+    CombPlane& P = args.plane[pl];
+    P.W = pl ? (clip->width >> clip->log_uvx) : clip->width;
+    P.H = pl ? (clip->height >> clip->log_uvy) : clip->height;
+    P.tilesX = (P.W + kCombTW - 1) / kCombTW; P.tilesY = (P.H + kCombTH - 1) / kCombTH;
+    P.tile0 = tile0; tile0 += P.tilesX * P.tilesY;
+    P.cls = pl ? 1 : 0;
+    const int thM = pl ? prm->th_move_c : prm->th_move_y;
+    const int thS = pl ? prm->th_shima_c : prm->th_shima_y, thL = pl ? prm->th_lshima_c : prm->th_lshima_y;
+    P.thM = (unsigned)(0x80 - thM) * 0x01010101u;
+    P.thS = (unsigned)thS * 0x00010001u;       // integer k in [1,2047] IS the fp16 bit pattern of k*2^-24
+    P.thL = (unsigned)thL * 0x00010001u;
+    const long long off = pl == 0 ? 0 : (pl == 1 ? clip->off_u : clip->off_v);
+    const int pitch = pl ? clip->pitch_uv : clip->pitch_y;
+    cuuint64_t gdim[3] = { (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)win.count };
+    cuuint64_t gstr[2] = { (cuuint64_t)pitch, (cuuint64_t)clip->frame_stride };
+    cuuint32_t box[3] = { (cuuint32_t)kCombTW, (cuuint32_t)kCombBoxH, 1u };
+    cuuint32_t estr[3] = { 1u, 1u, 1u };
+    CUresult r = ctx->encode_tiled(&args.map[pl], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                                   const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) AMTK_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  }
+  const int ntiles = tile0;
+  const int nf = hi - lo;
+  // ---- static weighted partition of (tile, frame) pairs over the resident CTAs ----
+  int occ = 0;
+  AMTK_CUDA(cudaFuncSetAttribute(comb_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombSmemBytes));
+  AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, comb_u8_kernel, kCombThreads, kCombSmemBytes));
+  if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
+  std::vector<long long> wt((size_t)ntiles);
+  long long total = 0;
+  for (int pl = 0; pl < 3; ++pl) {
+    const CombPlane& P = args.plane[pl];
+    for (int ty = 0; ty < P.tilesY; ++ty)
+      for (int tx = 0; tx < P.tilesX; ++tx) {
+        // cost model: live 16-row runs x 128-byte rows (a partially covered tile still computes whole runs);
+        // a constant per tile-frame stands for the barrier/reduction overhead
+        const int rows = std::min(kCombTH, P.H - ty * kCombTH);
+        const int runs = (rows + kCombR - 1) / kCombR;
+        const long long c = (long long)runs * kCombR * kCombTW + 2048;
+        wt[P.tile0 + ty * P.tilesX + tx] = c;
+        total += c * nf;
+      }
+  }
+  const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (long long)ntiles * nf);
+  std::vector<CombSegment> segs;
+  std::vector<int> seg_start((size_t)grid + 1, 0);
+  {
+    int b = 0; long long acc = 0;                       // acc = weight handed to CTAs [0,b] so far
+    long long target = (total * (b + 1)) / grid;
+    for (int t = 0; t < ntiles; ++t) {
+      int f = 0;
+      while (f < nf) {
+        // how many frames of this tile still fit into CTA b's share
+        long long room = target - acc;
+        int take = (int)std::min<long long>(nf - f, std::max<long long>(1, (room + wt[t] / 2) / wt[t]));
+        if (b == grid - 1) take = nf - f;
+        segs.push_back(CombSegment{ t, lo - win.first + f, lo - win.first + f + take });
+        acc += wt[t] * take; f += take;
+        while (b < grid - 1 && acc >= target) { ++b; seg_start[b] = (int)segs.size(); target = (total * (b + 1)) / grid; }
+      }
+    }
+    for (int i = b + 1; i <= grid; ++i) seg_start[i] = (int)segs.size();
+  }
+  const size_t seg_bytes = segs.size() * sizeof(CombSegment), st_bytes = seg_start.size() * sizeof(int);
+  const size_t st_off = (seg_bytes + 255) & ~(size_t)255;
+  if (!ensure(&ctx->small, &ctx->small_bytes, st_off + st_bytes)) return 0;
+  AMTK_CUDA(cudaMemcpyAsync(ctx->small, segs.data(), seg_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  AMTK_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->small) + st_off, seg_start.data(), st_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // pageable host vectors: the async copies above have completed their host reads on return
+  args.segs = reinterpret_cast<const CombSegment*>(ctx->small);
+  args.seg_start = reinterpret_cast<const int*>(reinterpret_cast<uint8_t*>(ctx->small) + st_off);
+  args.counts = dcounts;
+  args.out_frame0 = out_row0 - win.first;
+  AMTK_CUDA(cudaMemsetAsync(dcounts + (size_t)(lo - out_row0) * 12, 0, (size_t)nf * 12 * sizeof(int), ctx->stream));
+  comb_u8_kernel<<<grid, kCombThreads, kCombSmemBytes, ctx->stream>>>(args);
+  AMTK_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return 1;
+}
+
+static std::once_flag g_driver_once;
+static amtk_encode_tiled_fn g_encode = nullptr;
+
+}  // namespace amtk
+
+using namespace amtk;
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+extern "C" {
+
+const char* amtk_last_error(void) { return g_error.c_str(); }
+int amtk_version(void) { return 100; }
+
+int amtk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
+  if (!out) AMTK_FAIL("amtk_ctx_create: out is null");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); AMTK_FAIL("no CUDA device: this library has no CPU fallback"); }
+  if (device < 0 || device >= n) AMTK_FAIL("amtk_ctx_create: bad device ordinal");
+  int prev = 0; AMTK_CUDA(cudaGetDevice(&prev));
+  AMTK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop; AMTK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { cudaSetDevice(prev); AMTK_FAIL("this build targets sm_100a (Blackwell B200) only"); }
+  amtk_ctx* c = new amtk_ctx();
+  c->device = device; c->sm_count = prop.multiProcessorCount;
+  // NULL selects the legacy default stream (which orders with every blocking stream, e.g. torch's default one)
+  c->stream = reinterpret_cast<cudaStream_t>(cuda_stream); c->own_stream = false;
+  bool ok = cuda_ok(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+  for (int b = 0; b < 2 && ok; ++b) {
+    ok = cuda_ok(cudaEventCreateWithFlags(&c->ev_copy[b], cudaEventDisableTiming), "cudaEventCreate") &&
+         cuda_ok(cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming), "cudaEventCreate");
+  }
+  std::call_once(g_driver_once, [] {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<amtk_encode_tiled_fn>(fn);
+    else cudaGetLastError();
+  });
+  c->encode_tiled = g_encode;
+  cudaSetDevice(prev);
+  if (!ok) { amtk_ctx_destroy(c); return 0; }
+  *out = c;
+  return 1;
+}
+
+void amtk_ctx_destroy(amtk_ctx* c) {
+  if (!c) return;
+  int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (int b = 0; b < 2; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->stage[b]) cudaFree(c->stage[b]); }
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->small) cudaFree(c->small);
+  if (c->dout) cudaFree(c->dout);
+  if (c->dout2) cudaFree(c->dout2);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  cudaSetDevice(prev);
+  delete c;
+}
+
+int amtk_ctx_synchronize(amtk_ctx* c) {
+  if (!c) AMTK_FAIL("null context");
+  DevSelect ds(c); if (!ds.ok) return 0;
+  AMTK_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+int64_t amtk_ctx_launch_count(const amtk_ctx* c) { return c ? c->launches : 0; }
+
+int amtk_host_alloc(size_t bytes, void** out) {
+  if (!out) AMTK_FAIL("amtk_host_alloc: out is null");
+  AMTK_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 1;
+}
+void amtk_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------------------------------
+// logos
+// ---------------------------------------------------------------------------------------------------------
+static void logo_free_device(amtk_logo* l) {
+  float* fp[] = { l->dA, l->dB, l->dAU, l->dBU, l->dAV, l->dBV, l->dTapsT };
+  for (float* p : fp) if (p) cudaFree(p);
+  if (l->dPix) cudaFree(l->dPix);
+  if (l->dScales) cudaFree(l->dScales);
+  l->dA = l->dB = l->dAU = l->dBU = l->dAV = l->dBV = l->dTapsT = nullptr; l->dPix = nullptr; l->dScales = nullptr;
+}
+
+static int logo_upload_planes(amtk_logo* l) {
+  amtk::HostLogo& h = l->host;
+  const size_t ny = h.ySize() * sizeof(float), nc = h.cSize() * sizeof(float);
+  float** dst[6] = { &l->dA, &l->dB, &l->dAU, &l->dBU, &l->dAV, &l->dBV };
+  const float* src[6] = { h.aY(), h.bY(), h.aU(), h.bU(), h.aV(), h.bV() };
+  for (int i = 0; i < 6; ++i) {
+    const size_t n = i < 2 ? ny : nc;
+    AMTK_CUDA(cudaMalloc(dst[i], std::max<size_t>(n, 16)));
+    AMTK_CUDA(cudaMemcpy(*dst[i], src[i], n, cudaMemcpyHostToDevice));
+  }
+  return 1;
+}
+
+static int logo_upload_tables(amtk_logo* l) {
+  amtk::HostLogo& h = l->host;
+  if (l->dPix) { cudaFree(l->dPix); l->dPix = nullptr; }
+  if (l->dTapsT) { cudaFree(l->dTapsT); l->dTapsT = nullptr; }
+  if (l->dScales) { cudaFree(l->dScales); l->dScales = nullptr; }
+  const int count = h.count();
+  if (count > 0) {
+    std::vector<float> tapsT((size_t)25 * l->countPad, 0.0f);
+    for (int c = 0; c < count; ++c) for (int t = 0; t < 25; ++t) tapsT[(size_t)t * l->countPad + c] = h.kernels[(size_t)c * 25 + t];
+    AMTK_CUDA(cudaMalloc(&l->dPix, (size_t)count * sizeof(uint32_t)));
+    AMTK_CUDA(cudaMalloc(&l->dTapsT, tapsT.size() * sizeof(float)));
+    AMTK_CUDA(cudaMalloc(&l->dScales, (size_t)count * 32 * sizeof(float2)));
+    AMTK_CUDA(cudaMemcpy(l->dPix, h.pix.data(), (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    AMTK_CUDA(cudaMemcpy(l->dTapsT, tapsT.data(), tapsT.size() * sizeof(float), cudaMemcpyHostToDevice));
+    AMTK_CUDA(cudaMemcpy(l->dScales, h.scales.data(), (size_t)count * 32 * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  l->tables_uploaded = true;
+  return 1;
+}
+
+// Logos are host objects; their HBM copies are made on first use by a context (and stay on that device).
+static int logo_ensure_device(const amtk_logo* cl, amtk_ctx* ctx, bool need_tables) {
+  amtk_logo* l = const_cast<amtk_logo*>(cl);
+  std::lock_guard<std::mutex> lock(l->mu);
+  if (l->ctx && l->ctx->device != ctx->device) AMTK_FAIL("logo already resident on another device");
+  if (!l->ctx) l->ctx = ctx;
+  if (!l->dA && !logo_upload_planes(l)) return 0;
+  if (need_tables) {
+    if (!l->has_mask) AMTK_FAIL("logo has no mask: call amtk_logo_create_mask first");
+    if (!l->tables_uploaded && !logo_upload_tables(l)) return 0;
+  }
+  return 1;
+}
+
+static int logo_adopt(amtk_ctx* ctx, amtk::HostLogo&& h, amtk_logo** out) {
+  amtk_logo* l = new amtk_logo();
+  l->ctx = ctx; l->host = std::move(h);
+  *out = l;
+  return 1;
+}
+
+int amtk_logo_create(amtk_ctx* ctx, const float* data, int w, int h, int lx, int ly, int imgw, int imgh, int imgx, int imgy, amtk_logo** out) {
+  if (!data || !out) AMTK_FAIL("amtk_logo_create: null argument");   // ctx may be NULL: bound on first use
+  if (w < 5 || h < 5 || w > 4096 || h > 4096 || lx < 0 || lx > 2 || ly < 0 || ly > 2) AMTK_FAIL("amtk_logo_create: bad logo geometry");
+  amtk::HostLogo hl; hl.init(w, h, lx, ly, imgw, imgh, imgx, imgy);
+  memcpy(hl.data.data(), data, hl.dataSize() * sizeof(float));
+  return logo_adopt(ctx, std::move(hl), out);
+}
+
+int amtk_logo_load(amtk_ctx* ctx, const char* path, amtk_logo** out, void* header540) {
+  if (!path || !out) AMTK_FAIL("amtk_logo_load: null argument");
+  amtk::HostLogo hl; amtk::LgdHeader hdr; std::string err;
+  if (!amtk::lgd_load(path, hl, &hdr, err)) AMTK_FAIL(err);
+  if (header540) memcpy(header540, &hdr, sizeof(hdr));
+  return logo_adopt(ctx, std::move(hl), out);
+}
+
+int amtk_logo_save(const amtk_logo* l, const char* path, const char* name, int service_id) {
+  if (!l || !path) AMTK_FAIL("amtk_logo_save: null argument");
+  std::string err;
+  if (!amtk::lgd_save(l->host, path, name ? name : "No Name", service_id, err)) AMTK_FAIL(err);
+  return 1;
+}
+
+void amtk_logo_destroy(amtk_logo* l) {
+  if (!l) return;
+  if (l->ctx && l->dA) { DevSelect ds(l->ctx); logo_free_device(l); }
+  delete l;
+}
+
+int amtk_logo_deint(const amtk_logo* src, amtk_logo** out) {
+  if (!src || !out) AMTK_FAIL("amtk_logo_deint: null argument");
+  amtk::HostLogo d; amtk::logo_deint(src->host, d);
+  return logo_adopt(src->ctx, std::move(d), out);
+}
+
+int amtk_logo_field(const amtk_logo* src, int bottom, amtk_logo** out) {
+  if (!src || !out) AMTK_FAIL("amtk_logo_field: null argument");
+  if (src->host.h / 2 < 5) AMTK_FAIL("amtk_logo_field: logo too small");
+  amtk::HostLogo f; amtk::logo_field(src->host, bottom != 0, f);
+  return logo_adopt(src->ctx, std::move(f), out);
+}
+
+int amtk_logo_create_mask(amtk_logo* l, float maskratio) {
+  if (!l) AMTK_FAIL("amtk_logo_create_mask: null logo");
+  if (!(maskratio > 0.0f) || maskratio > 1.0f) AMTK_FAIL("amtk_logo_create_mask: maskratio must be in (0,1]");
+  std::lock_guard<std::mutex> lock(l->mu);
+  amtk::logo_create_mask(l->host, maskratio);
+  l->countPad = std::max(32, (l->host.count() + 31) & ~31);
+  l->has_mask = true;
+  l->tables_uploaded = false;       // (re)uploaded by the next evaluation call
+  return 1;
+}
+
+int amtk_logo_get_info(const amtk_logo* l, amtk_logo_info* o) {
+  if (!l || !o) AMTK_FAIL("amtk_logo_get_info: null argument");
+  const amtk::HostLogo& h = l->host;
+  o->w = h.w; o->h = h.h; o->log_uvx = h.logUVx; o->log_uvy = h.logUVy;
+  o->imgw = h.imgw; o->imgh = h.imgh; o->imgx = h.imgx; o->imgy = h.imgy;
+  o->maskpixels = h.maskpixels; o->count = h.count(); o->black_score = h.blackScore;
+  return 1;
+}
+
+int amtk_logo_get_tables(const amtk_logo* l, float* data, uint8_t* mask, float* kernels, float* scales) {
+  if (!l) AMTK_FAIL("amtk_logo_get_tables: null logo");
+  const amtk::HostLogo& h = l->host;
+  if (data) memcpy(data, h.data.data(), h.dataSize() * sizeof(float));
+  if ((mask || kernels || scales) && !l->has_mask) AMTK_FAIL("logo has no mask");
+  if (mask) memcpy(mask, h.mask.data(), h.mask.size());
+  if (kernels) memcpy(kernels, h.kernels.data(), h.kernels.size() * sizeof(float));
+  if (scales) memcpy(scales, h.scales.data(), h.scales.size() * sizeof(float));
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// evaluation entry points
+// ---------------------------------------------------------------------------------------------------------
+static int finish_output(amtk_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, int out_on_device) {
+  if (out_on_device) return 1;
+  AMTK_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+static int scan_frames_impl(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
+                            const Window& win, int lo, int hi, int pitch_override, float* dscores, int row0) {
+  static const float kFades01[2] = { 0.0f, 1.0f };
+  const int pitch = pitch_override > 0 ? pitch_override : clip->pitch_y / clip->bytes_per_sample;
+  for (int i = 0; i < nlogos; ++i) {
+    const amtk_logo* lg = logos[i];
+    float* o = dscores + (size_t)(lo - row0) * nlogos * 2;
+    if (!lg || lg->host.imgw != clip->width || lg->host.imgh != clip->height) {      // LogoScan.hpp:1551-1558
+      fill_pairs_kernel<<<(hi - lo + 127) / 128, 128, 0, ctx->stream>>>(o, hi - lo, nlogos * 2, i * 2, 0.0f, -1.0f);
+      AMTK_CUDA(cudaGetLastError()); ctx->launches += 1;
+      continue;
+    }
+    if (!roi_inside(lg->host, clip, pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
+    EvalSpec sp{ lg, lg->host.imgx, lg->host.imgy, lg->host.w, lg->host.h, 0, 0, lg->host.w, 2, kFades01, 0, i * 2, 1 };
+    if (!launch_eval(ctx, clip, win, lo, hi, pitch, sp, dscores, nlogos * 2, row0)) return 0;
+  }
+  return 1;
+}
+
+int amtk_logo_scan_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
+                          int frame0, int nframes, int pitch_override, float* out, int out_on_device) {
+  if (!ctx || !logos || !out || nlogos < 1) AMTK_FAIL("amtk_logo_scan_frames: bad argument");
+  if (!validate_clip(clip, false)) return 0;
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  const size_t bytes = (size_t)nframes * nlogos * 2 * sizeof(float);
+  float* d = out;
+  if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
+  if (!for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
+        return scan_frames_impl(ctx, clip, logos, nlogos, w, lo, hi, pitch_override, d, frame0); }))
+    return 0;
+  return finish_output(ctx, out, d, bytes, out_on_device);
+}
+
+static int analyze_impl(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* dl, const amtk_logo* ft, const amtk_logo* fb,
+                        const Window& win, int lo, int hi, float* dout, int row0) {
+  float fades[11];
+  for (int f = 0; f <= 10; ++f) fades[f] = (float)f / 10.0f;             // LogoScan.hpp:1152
+  const int pitch = clip->pitch_y / clip->bytes_per_sample;
+  const int w = dl->host.w, h = dl->host.h;
+  if (!roi_inside(dl->host, clip, pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
+  const int rx = dl->host.imgx, ry = dl->host.imgy;
+  EvalSpec sp{ dl, rx, ry, w, h, 0, 0, w, 11, fades, 1, 0, 1 };                // p[f]: deint logo on DeintY
+  EvalSpec st{ ft, rx, ry, w, h, 1, 0, 2 * w, 11, fades, 1, 11, 1 };           // t[f]: top field logo on CopyY, stride 2w
+  EvalSpec sb{ fb, rx, ry, w, h, 1, w, 2 * w, 11, fades, 1, 22, 1 };           // b[f]: bottom field logo on CopyY + w
+  return launch_eval(ctx, clip, win, lo, hi, pitch, sp, dout, 33, row0) &&
+         launch_eval(ctx, clip, win, lo, hi, pitch, st, dout, 33, row0) &&
+         launch_eval(ctx, clip, win, lo, hi, pitch, sb, dout, 33, row0);
+}
+
+int amtk_logo_analyze_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* dl, const amtk_logo* ft, const amtk_logo* fb,
+                             int frame0, int nframes, float* out, int out_on_device) {
+  if (!ctx || !dl || !ft || !fb || !out) AMTK_FAIL("amtk_logo_analyze_frames: bad argument");
+  if (!validate_clip(clip, false)) return 0;
+  if (ft->host.w != dl->host.w || fb->host.w != dl->host.w || ft->host.h != dl->host.h / 2 || fb->host.h != dl->host.h / 2)
+    AMTK_FAIL("field logos do not match the deint logo");
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  const size_t bytes = (size_t)nframes * 33 * sizeof(float);
+  float* d = out;
+  if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
+  if (!for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
+        return analyze_impl(ctx, clip, dl, ft, fb, w, lo, hi, d, frame0); }))
+    return 0;
+  return finish_output(ctx, out, d, bytes, out_on_device);
+}
+
+int amtk_logo_eval_fades(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* dl, const float* fades, int nfades,
+                         int frame0, int nframes, float* out, int out_on_device) {
+  if (!ctx || !dl || !fades || !out) AMTK_FAIL("amtk_logo_eval_fades: bad argument");
+  if (nfades < 1 || nfades > kMaxFades) AMTK_FAIL("amtk_logo_eval_fades: 1..24 fade levels");
+  if (!validate_clip(clip, false)) return 0;
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  const size_t bytes = (size_t)nframes * nfades * sizeof(float);
+  float* d = out;
+  if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
+  const int pitch = clip->pitch_y / clip->bytes_per_sample;
+  if (!roi_inside(dl->host, clip, pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
+  EvalSpec sp{ dl, dl->host.imgx, dl->host.imgy, dl->host.w, dl->host.h, 0, 0, dl->host.w, nfades, fades, 0, 0, 1 };
+  if (!for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
+        return launch_eval(ctx, clip, w, lo, hi, pitch, sp, d, nfades, frame0); }))
+    return 0;
+  return finish_output(ctx, out, d, bytes, out_on_device);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// combing metric + fused step
+// ---------------------------------------------------------------------------------------------------------
+void amtk_comb_default_params(amtk_comb_params* p) {
+  if (!p) return;
+  p->th_move_y = 20; p->th_shima_y = 12; p->th_lshima_y = 36;
+  p->th_move_c = 24; p->th_shima_c = 16; p->th_lshima_c = 48;
+}
+
+int amtk_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_comb_params* prm, int frame0, int nframes,
+                     int32_t* counts, int out_on_device) {
+  if (!ctx || !prm || !counts) AMTK_FAIL("amtk_comb_frames: bad argument");
+  if (!validate_clip(clip, true) || !comb_thresholds_ok(prm)) return 0;
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  const size_t bytes = (size_t)nframes * 12 * sizeof(int32_t);
+  int* d = counts;
+  if (!out_on_device) { if (!ensure(&ctx->dout2, &ctx->dout2_bytes, bytes)) return 0; d = reinterpret_cast<int*>(ctx->dout2); }
+  if (!for_each_window(ctx, clip, frame0, nframes, true, [&](const Window& w, int lo, int hi) {
+        return launch_comb(ctx, clip, w, lo, hi, prm, d, frame0); }))
+    return 0;
+  return finish_output(ctx, counts, d, bytes, out_on_device);
+}
+
+int amtk_scan_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
+                          const amtk_comb_params* prm, int frame0, int nframes, float* scores, int32_t* counts, int out_on_device) {
+  if (!ctx || !prm || !counts || !scores || !logos || nlogos < 1) AMTK_FAIL("amtk_scan_comb_frames: bad argument");
+  if (!validate_clip(clip, true) || !comb_thresholds_ok(prm)) return 0;
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  const size_t sbytes = (size_t)nframes * nlogos * 2 * sizeof(float), cbytes = (size_t)nframes * 12 * sizeof(int32_t);
+  float* ds_ = scores; int* dc = counts;
+  if (!out_on_device) {
+    if (!ensure(&ctx->dout, &ctx->dout_bytes, sbytes) || !ensure(&ctx->dout2, &ctx->dout2_bytes, cbytes)) return 0;
+    ds_ = reinterpret_cast<float*>(ctx->dout); dc = reinterpret_cast<int*>(ctx->dout2);
+  }
+  if (!for_each_window(ctx, clip, frame0, nframes, true, [&](const Window& w, int lo, int hi) {
+        return launch_comb(ctx, clip, w, lo, hi, prm, dc, frame0) &&
+               scan_frames_impl(ctx, clip, logos, nlogos, w, lo, hi, 0, ds_, frame0); }))
+    return 0;
+  if (out_on_device) return 1;
+  AMTK_CUDA(cudaMemcpyAsync(scores, ds_, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AMTK_CUDA(cudaMemcpyAsync(counts, dc, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LogoScan accumulation
+// ---------------------------------------------------------------------------------------------------------
+int amtk_scan_create(amtk_ctx* ctx, int scanw, int scanh, int lx, int ly, int thy, amtk_scan** out) {
+  if (!ctx || !out) AMTK_FAIL("amtk_scan_create: null argument");
+  if (scanw < 4 || scanh < 4 || scanw > 4096 || scanh > 4096 || lx < 0 || lx > 2 || ly < 0 || ly > 2) AMTK_FAIL("amtk_scan_create: bad geometry");
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  amtk_scan* s = new amtk_scan();
+  s->ctx = ctx; s->scanw = scanw; s->scanh = scanh; s->logUVx = lx; s->logUVy = ly; s->thy = thy;
+  s->npix = (size_t)scanw * scanh + 2 * (size_t)(scanw >> lx) * (scanh >> ly);
+  if (!cuda_ok(cudaMalloc(&s->dSums, s->npix * 3 * sizeof(unsigned long long)), "cudaMalloc") ||
+      !cuda_ok(cudaMalloc(&s->dBg, 8 * sizeof(unsigned long long)), "cudaMalloc")) { amtk_scan_destroy(s); return 0; }
+  cudaMemset(s->dSums, 0, s->npix * 3 * sizeof(unsigned long long));
+  cudaMemset(s->dBg, 0, 8 * sizeof(unsigned long long));
+  *out = s;
+  return 1;
+}
+
+void amtk_scan_destroy(amtk_scan* s) {
+  if (!s) return;
+  { DevSelect ds(s->ctx); if (s->dSums) cudaFree(s->dSums); if (s->dBg) cudaFree(s->dBg); }
+  delete s;
+}
+
+int amtk_scan_add_frames(amtk_scan* s, const amtk_clip* clip, int scanx, int scany, int frame0, int nframes,
+                         const uint8_t* frame_select, uint8_t* valid_out) {
+  if (!s) AMTK_FAIL("amtk_scan_add_frames: null scan");
+  amtk_ctx* ctx = s->ctx;
+  if (!validate_clip(clip, true)) return 0;
+  if (clip->bytes_per_sample != 1) AMTK_FAIL("LogoScan supports 8-bit clips only (as the reference, LogoScan.hpp:812)");
+  if (clip->log_uvx != s->logUVx || clip->log_uvy != s->logUVy) AMTK_FAIL("chroma subsampling mismatch");
+  if (scanx < 0 || scany < 0 || scanx + s->scanw > clip->width || scany + s->scanh > clip->height) AMTK_FAIL("scan rectangle outside the frame");
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  // small per-frame buffers: int4 bg[n], u8 select[n], u8 valid[n]
+  const size_t bg_bytes = (size_t)nframes * sizeof(int4), off_sel = (bg_bytes + 255) & ~(size_t)255;
+  const size_t off_val = off_sel + (((size_t)nframes + 255) & ~(size_t)255);
+  if (!ensure(&ctx->dout, &ctx->dout_bytes, off_val + (size_t)nframes + 256)) return 0;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->dout);
+  int4* dbg = reinterpret_cast<int4*>(base); uint8_t* dsel = base + off_sel; uint8_t* dval = base + off_val;
+  if (frame_select) AMTK_CUDA(cudaMemcpyAsync(dsel, frame_select, (size_t)nframes, cudaMemcpyHostToDevice, ctx->stream));
+  const int ok = for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
+    ScanClip c;
+    c.base = w.dev_base; c.frame_stride = clip->frame_stride; c.offU = clip->off_u; c.offV = clip->off_v;
+    c.pitchY = clip->pitch_y; c.pitchUV = clip->pitch_uv;
+    c.scanx = scanx; c.scany = scany; c.scanw = s->scanw; c.scanh = s->scanh; c.logUVx = s->logUVx; c.logUVy = s->logUVy; c.thy = s->thy;
+    c.frame0 = lo - w.first; c.nframes = hi - lo;
+    const int rel = lo - frame0;
+    scan_border_kernel<<<hi - lo, 256, 0, ctx->stream>>>(c, frame_select ? dsel + rel : nullptr, dbg + rel);
+    AMTK_CUDA(cudaGetLastError());
+    const int pixblocks = (int)((s->npix + 255) / 256);
+    const int splits = std::max(1, std::min(hi - lo, (ctx->sm_count * 8) / pixblocks));
+    scan_accumulate_kernel<<<dim3(pixblocks, splits), 256, 0, ctx->stream>>>(c, dbg + rel, s->dSums, s->dBg, dval + rel);
+    AMTK_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    return 1;
+  });
+  if (!ok) return 0;
+  std::vector<uint8_t> tmp;
+  unsigned long long nv = 0;
+  if (valid_out) AMTK_CUDA(cudaMemcpyAsync(valid_out, dval, (size_t)nframes, cudaMemcpyDeviceToHost, ctx->stream));
+  AMTK_CUDA(cudaMemcpyAsync(&nv, s->dBg + 6, sizeof(nv), cudaMemcpyDeviceToHost, ctx->stream));
+  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->nvalid = (int)nv;
+  return 1;
+}
+
+int amtk_scan_num_valid(const amtk_scan* s) { return s ? s->nvalid : 0; }
+
+int amtk_scan_get_sums(amtk_scan* s, double* out) {
+  if (!s || !out) AMTK_FAIL("amtk_scan_get_sums: null argument");
+  DevSelect ds(s->ctx); if (!ds.ok) return 0;
+  std::vector<unsigned long long> h(s->npix * 3), bg(8);
+  AMTK_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  AMTK_CUDA(cudaMemcpy(h.data(), s->dSums, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  AMTK_CUDA(cudaMemcpy(bg.data(), s->dBg, bg.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  const size_t ny = (size_t)s->scanw * s->scanh, nc = (size_t)(s->scanw >> s->logUVx) * (s->scanh >> s->logUVy);
+  for (size_t i = 0; i < s->npix; ++i) {
+    const int pl = i < ny ? 0 : (i < ny + nc ? 1 : 2);
+    out[i * 5 + 0] = (double)h[i * 3 + 0];        // sumF   (exact: < 2^53)
+    out[i * 5 + 1] = (double)bg[pl * 2 + 0];      // sumB
+    out[i * 5 + 2] = (double)h[i * 3 + 1];        // sumF2
+    out[i * 5 + 3] = (double)bg[pl * 2 + 1];      // sumB2
+    out[i * 5 + 4] = (double)h[i * 3 + 2];        // sumFB
+  }
+  s->nvalid = (int)bg[6];
+  return 1;
+}
+
+int amtk_scan_get_logo(amtk_scan* s, int maxv, int clean, float* data) {
+  if (!s || !data) AMTK_FAIL("amtk_scan_get_logo: null argument");
+  std::vector<double> sums(s->npix * 5);
+  if (!amtk_scan_get_sums(s, sums.data())) return 0;
+  if (!amtk::scan_finalize(sums.data(), s->nvalid, s->scanw, s->scanh, s->logUVx, s->logUVy, maxv, clean != 0, data))
+    AMTK_FAIL("Insufficient logo frames");
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// erase
+// ---------------------------------------------------------------------------------------------------------
+int amtk_erase_logo_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* logo, int frame0, int nframes, const float* fades) {
+  if (!ctx || !logo || !fades) AMTK_FAIL("amtk_erase_logo_frames: bad argument");
+  if (!validate_clip(clip, true)) return 0;
+  if (!clip->on_device) AMTK_FAIL("amtk_erase_logo_frames: clip must be device resident (frames are edited in place in HBM)");
+  const amtk::HostLogo& h = logo->host;
+  if (h.imgx < 0 || h.imgy < 0 || h.imgx + h.w > clip->width || h.imgy + h.h > clip->height) AMTK_FAIL("logo rectangle lies outside the frame");
+  if (frame0 < 0 || nframes < 0 || frame0 + nframes > clip->num_frames) AMTK_FAIL("frame range outside the clip");
+  if (nframes == 0) return 1;
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  if (!logo_ensure_device(logo, ctx, false)) return 0;
+  if (!ensure(&ctx->dout, &ctx->dout_bytes, (size_t)nframes * 2 * sizeof(float))) return 0;
+  AMTK_CUDA(cudaMemcpyAsync(ctx->dout, fades, (size_t)nframes * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  EraseJob j;
+  j.base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(clip->base)); j.frame_stride = clip->frame_stride;
+  j.offU = clip->off_u; j.offV = clip->off_v;
+  j.pitchY = clip->pitch_y / clip->bytes_per_sample; j.pitchUV = clip->pitch_uv / clip->bytes_per_sample;
+  j.frame0 = frame0; j.nframes = nframes;
+  j.w = h.w; j.h = h.h; j.logUVx = h.logUVx; j.logUVy = h.logUVy; j.imgx = h.imgx; j.imgy = h.imgy;
+  j.aY = logo->dA; j.bY = logo->dB; j.aU = logo->dAU; j.bU = logo->dBU; j.aV = logo->dAV; j.bV = logo->dBV;
+  j.fades = reinterpret_cast<const float*>(ctx->dout);
+  j.maxv = (float)((1 << clip->bits_per_sample) - 1);
+  if (clip->bytes_per_sample == 1) erase_logo_kernel<uint8_t><<<nframes, 256, 0, ctx->stream>>>(j);
+  else erase_logo_kernel<uint16_t><<<nframes, 256, 0, ctx->stream>>>(j);
+  AMTK_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));    // `fades` staging buffer is reused by later calls
+  return 1;
+}
+
+void amtk_calc_fade2(const float* records, int num_records, int num_frames, int n, float* ft, float* fb) {
+  amtk::calc_fade2(records, num_records, num_frames, n, ft, fb);
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// amtk_internal.h -- shared declarations of the CUDA translation unit (not part of the public ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/amtk_b200.h"
+#include "logo_host.h"
+
+// cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no link-time dependency on libcuda.so).
+typedef CUresult (*amtk_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+namespace amtk {
+
+void set_error(const std::string& msg);
+bool cuda_ok(cudaError_t e, const char* what);
+
+#define AMTK_CUDA(call)                                          \
+  do {                                                           \
+    if (!::amtk::cuda_ok((call), #call)) return 0;               \
+  } while (0)
+#define AMTK_FAIL(msg)                                           \
+  do {                                                           \
+    ::amtk::set_error(msg);                                      \
+    return 0;                                                    \
+  } while (0)
+
+// Evaluation tables of one logo as the kernels see them (all device pointers).
+struct LogoDev {
+  int w, h, count, countPad;      // countPad: kernel-tap row pitch (multiple of 32)
+  float blackScore;
+  const float* A;                 // w*h
+  const float* B;                 // w*h
+  const uint32_t* pix;            // count: x | y<<16, reference scan order
+  const float* tapsT;             // 25 x countPad, tap-major (coalesced one-time load into registers)
+  const float2* scales;           // count x 32 {scale, scale2}
+};
+
+}  // namespace amtk
+
+struct amtk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;       // H2D staging for host-resident clips
+  cudaEvent_t ev_copy[2] = { nullptr, nullptr };
+  cudaEvent_t ev_done[2] = { nullptr, nullptr };
+  int sm_count = 0;
+  int64_t launches = 0;
+  // scratch (grown on demand, reused across calls)
+  void* scratch = nullptr; size_t scratch_bytes = 0;       // per-pixel scores
+  void* stage[2] = { nullptr, nullptr }; size_t stage_bytes = 0;   // device staging of host clips
+  void* small = nullptr; size_t small_bytes = 0;           // misc small device buffers (counters, segments)
+  void* dout = nullptr; size_t dout_bytes = 0;             // device-side outputs when the caller's are on the host
+  void* dout2 = nullptr; size_t dout2_bytes = 0;
+  amtk_encode_tiled_fn encode_tiled = nullptr;
+};
+
+struct amtk_logo {
+  amtk_ctx* ctx = nullptr;
+  amtk::HostLogo host;
+  // device copies (valid after create_mask; A/B valid from creation)
+  float* dA = nullptr; float* dB = nullptr;       // Y planes
+  float* dAU = nullptr; float* dBU = nullptr; float* dAV = nullptr; float* dBV = nullptr;
+  uint32_t* dPix = nullptr; float* dTapsT = nullptr; float2* dScales = nullptr;
+  int countPad = 0;
+  bool has_mask = false;
+  bool tables_uploaded = false;
+  std::mutex mu;
+};
+
+struct amtk_scan {
+  amtk_ctx* ctx = nullptr;
+  int scanw = 0, scanh = 0, logUVx = 1, logUVy = 1, thy = 0;
+  int nvalid = 0;
+  unsigned long long* dSums = nullptr;     // [npix][3] u64: sumF, sumF2, sumFB  (exact integers)
+  unsigned long long* dBg = nullptr;       // [3 planes][2]: sumB, sumB2 (per plane scalars) + [6] = nvalid
+  size_t npix = 0;
+};

@@ -1,0 +1,241 @@
+// comb_kernels.cuh -- field-difference / combing metric, the full-frame streaming pass (HBM-read bound).
+//
+// Spec (integer, order independent => bit-exact by construction):
+//   comb(y,x) = | p[y-2] + 4 p[y] + p[y+2] - 3 (p[y-1] + p[y+1]) |            2 <= y < H-2
+//   shima[f] += comb >= thS ; lshima[f] += comb >= thL                         f = y & 1 (top / bottom field)
+//   move[f]  += | p_n[y][x] - p_{n-1}[y][x] | >= thM                           every row; prev(first) = itself
+//   per frame: int32[12] = [Y, C(=U+V)] x [top, bottom] x [move, shima, lshima]
+//
+// Design for sm_100a:
+//   * work unit = (plane tile of 128 px x 128 rows, run of consecutive frames).  A CTA streams the tile of frame
+//     n, n+1, ... through a 4-stage shared-memory ring filled by TMA (cp.async.bulk.tensor.3d, one instruction
+//     per tile incl. the +-2 row halo, out-of-frame rows/cols zero-filled by the TMA unit).  The tile of frame
+//     n-1 is still in the ring when frame n is processed, so the inter-frame difference costs no second HBM read:
+//     every frame byte is fetched from HBM once (plus 4/128 halo rows).
+//   * each thread owns an 8-pixel-wide column strip and walks 16 rows with a 5-row sliding window held in
+//     registers as fp16x2.  Bytes zero-extended into 16-bit lanes ARE exact fp16 values (subnormals, k*2^-24),
+//     so PRMT is the whole u8->f16 conversion, the 5-tap response (|.| <= 1530 < 2048) is exact in fp16, and
+//     HSET2.GE with |x| does the threshold on two pixels per instruction.  The inter-frame difference runs
+//     4 pixels per instruction (VABSDIFF4 + SWAR compare + IDP.4A count).  Tensor cores are not used: nothing
+//     here is a contraction.
+//   * counters: per-thread packed accumulators -> REDUX per warp -> shared -> 6 global RED per tile-frame.
+//   * static weighted partition of all (tile, frame) pairs over 148 x occupancy CTAs (host side): no tail.
+#pragma once
+#include <cuda_fp16.h>
+#include "amtk_internal.h"
+
+namespace amtk {
+
+constexpr int kCombTW = 128;            // tile width in bytes (= pixels for u8)
+constexpr int kCombTH = 128;            // tile height (output rows)
+constexpr int kCombR = 16;              // rows per thread run
+constexpr int kCombRuns = kCombTH / kCombR;   // 8
+constexpr int kCombThreads = (kCombTW / 8) * kCombRuns;   // 16 strips x 8 runs = 128
+constexpr int kCombBoxH = kCombTH + 4;  // with +-2 halo rows
+constexpr int kCombStageBytes = kCombTW * kCombBoxH;      // 16896
+constexpr int kCombStages = 4;
+constexpr int kCombSmemBytes = kCombStages * kCombStageBytes + 128;   // + alignment slack
+
+struct CombPlane {
+  int W, H;                 // plane size in pixels
+  int tilesX, tilesY;
+  int tile0;                // first tile id of this plane
+  int cls;                  // 0 = Y, 1 = C
+  unsigned thM, thS, thL;   // thM: SWAR byte constant (0x80-thM)*0x01010101; thS/thL: packed half2 bit patterns
+};
+
+struct CombSegment {        // a run of frames of one tile, processed by one CTA
+  int tile;                 // global tile id
+  int fbegin, fend;         // frame indices inside the device window
+};
+
+struct CombArgs {
+  CUtensorMap map[3];       // 3-D (x, y, frame) u8 views of the Y, U, V planes of the device window
+  CombPlane plane[3];
+  const CombSegment* segs;
+  const int* seg_start;     // [gridDim.x + 1]
+  int* counts;              // [nframes_out][12]
+  int out_frame0;           // counts row = frame - out_frame0
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers (mbarrier + TMA)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-thread tile-frame body
+// ---------------------------------------------------------------------------------------------------------
+struct H4 { __half2 v[4]; };    // 8 pixels of one row as fp16x2
+
+__device__ __forceinline__ H4 bytes_to_h4(uint2 raw) {
+  H4 r;
+  uint32_t a = __byte_perm(raw.x, 0, 0x4140), b = __byte_perm(raw.x, 0, 0x4342);
+  uint32_t c = __byte_perm(raw.y, 0, 0x4140), d = __byte_perm(raw.y, 0, 0x4342);
+  r.v[0] = *reinterpret_cast<__half2*>(&a); r.v[1] = *reinterpret_cast<__half2*>(&b);
+  r.v[2] = *reinterpret_cast<__half2*>(&c); r.v[3] = *reinterpret_cast<__half2*>(&d);
+  return r;
+}
+
+// bytes of d that are >= th (1 <= th <= 128): bit 7 of each byte of the result.  kM = (0x80 - th) * 0x01010101.
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t d, uint32_t kM) {
+  return (((d & 0x7F7F7F7Fu) + kM) | d) & 0x80808080u;
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
+                                               int y_first /* global y of this thread's first row */, int H,
+                                               uint32_t kM, uint32_t thS_bits, uint32_t thL_bits,
+                                               uint32_t& oS, uint32_t& oL, uint32_t& oM) {
+  // cur/prev point at this thread's strip in smem row (run*R) of the box, i.e. global row y_first-2.
+  const __half2 thS = *reinterpret_cast<const __half2*>(&thS_bits);
+  const __half2 thL = *reinterpret_cast<const __half2*>(&thL_bits);
+  const __half2 k4 = __float2half2_rn(4.0f), km3 = __float2half2_rn(-3.0f);
+  uint32_t accS[2] = { 0u, 0u }, accL[2] = { 0u, 0u }, accM[2] = { 0u, 0u };
+
+  uint2 raw_c = *reinterpret_cast<const uint2*>(cur + 2 * kCombTW);      // centre row of j=0
+  uint2 raw_n = *reinterpret_cast<const uint2*>(cur + 3 * kCombTW);
+  H4 h0 = bytes_to_h4(*reinterpret_cast<const uint2*>(cur));
+  H4 h1 = bytes_to_h4(*reinterpret_cast<const uint2*>(cur + kCombTW));
+  H4 h2 = bytes_to_h4(raw_c);
+  H4 h3 = bytes_to_h4(raw_n);
+#pragma unroll
+  for (int j = 0; j < kCombR; ++j) {
+    const uint2 raw_nn = *reinterpret_cast<const uint2*>(cur + (j + 4) * kCombTW);
+    const H4 h4 = bytes_to_h4(raw_nn);
+    const uint2 pv = *reinterpret_cast<const uint2*>(prev + (j + 2) * kCombTW);
+    const int f = j & 1;       // tile origin and run origin are even => field parity of the row is j&1
+    __half2 tS = thS, tL = thL;
+    if (EDGE) {
+      const int y = y_first + j;
+      if (y < 2 || y >= H - 2) { const uint32_t inf2 = 0x7C007C00u; tS = *reinterpret_cast<const __half2*>(&inf2); tL = tS; }
+    }
+    uint32_t mS[4], mL[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __half2 t = __hadd2(h0.v[q], h4.v[q]);
+      t = __hfma2(k4, h2.v[q], t);
+      const __half2 u = __hadd2(h1.v[q], h3.v[q]);
+      const __half2 r = __habs2(__hfma2(km3, u, t));
+      mS[q] = __hge2_mask(r, tS);
+      mL[q] = __hge2_mask(r, tL);
+    }
+    // 0xFFFF-per-lane masks are subtracted as plain 32-bit integers; decode_pair() undoes the lane coupling
+    accS[f] = accS[f] - mS[0] - mS[1]; accS[f] = accS[f] - mS[2] - mS[3];
+    accL[f] = accL[f] - mL[0] - mL[1]; accL[f] = accL[f] - mL[2] - mL[3];
+    // inter-frame difference of the centre row, 4 pixels per op
+    const uint32_t d0 = __vabsdiffu4(raw_c.x, pv.x), d1 = __vabsdiffu4(raw_c.y, pv.y);
+    accM[f] = __dp4a(bytes_ge(d0, kM), 0x01010101u, accM[f]);
+    accM[f] = __dp4a(bytes_ge(d1, kM), 0x01010101u, accM[f]);
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4; raw_c = raw_n; raw_n = raw_nn;
+  }
+  // acc = cl + 65536*(ch - cl) (mod 2^32) for lane counts cl, ch  =>  cl + ch = hi16 + 2*lo16
+  auto decode_pair = [](uint32_t a) { return ((a >> 16) + 2u * (a & 0xFFFFu)) & 0xFFFFu; };
+  oS = decode_pair(accS[0]) | (decode_pair(accS[1]) << 16);       // top | bottom<<16
+  oL = decode_pair(accL[0]) | (decode_pair(accL[1]) << 16);
+  oM = (accM[0] >> 7) | ((accM[1] >> 7) << 16);                   // dp4a summed 0x80 per hit
+}
+
+__global__ void __launch_bounds__(kCombThreads, 3) comb_u8_kernel(const __grid_constant__ CombArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte aligned ring base; pointer arithmetic stays on the __shared__ array so loads compile to LDS
+  uint8_t* tiles = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  __shared__ __align__(8) uint64_t full_bar[kCombStages];
+  __shared__ unsigned int red[2][3];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int strip = tid & 15, run = tid >> 4;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kCombStages; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 6) (&red[0][0])[tid] = 0u;
+  __syncthreads();
+
+  uint32_t gload = 0;      // loads consumed so far by this CTA (ring position of L_0 of the current segment)
+  uint32_t gstep = 0;      // tile-frames processed so far (selects the red[] buffer)
+  const int seg_lo = a.seg_start[blockIdx.x], seg_hi = a.seg_start[blockIdx.x + 1];
+  for (int si = seg_lo; si < seg_hi; ++si) {
+    const CombSegment seg = a.segs[si];
+    const int pl = (seg.tile >= a.plane[2].tile0) ? 2 : (seg.tile >= a.plane[1].tile0) ? 1 : 0;
+    const CombPlane& P = a.plane[pl];
+    const CUtensorMap* map = &a.map[pl];
+    const int lt = seg.tile - P.tile0;
+    const int ty = lt / P.tilesX, tx = lt - ty * P.tilesX;
+    const int x0 = tx * kCombTW, y0 = ty * kCombTH;
+    const int nf = seg.fend - seg.fbegin;
+    const int nloads = nf + 1;                       // L_0 = previous frame, L_k = frame fbegin+k-1
+    const int fprev = seg.fbegin > 0 ? seg.fbegin - 1 : seg.fbegin;
+    const bool edge = (y0 < 2) || (y0 + kCombTH + 2 > P.H);
+    const bool rows_live = (y0 + run * kCombR) < P.H;      // thread's run intersects the plane
+
+    auto issue = [&](int j) {                        // thread 0 only
+      const uint32_t g = gload + (uint32_t)j;
+      const int st = g % kCombStages;
+      const int fr = (j == 0) ? fprev : seg.fbegin + j - 1;
+      mbar_expect_tx(&full_bar[st], kCombStageBytes);
+      tma_load_3d(tiles + st * kCombStageBytes, map, &full_bar[st], x0, y0 - 2, fr);
+    };
+    if (tid == 0) {
+      const int pro = nloads < kCombStages ? nloads : kCombStages;
+      for (int j = 0; j < pro; ++j) issue(j);
+    }
+    mbar_wait(&full_bar[gload % kCombStages], (gload / kCombStages) & 1u);      // L_0
+    for (int k = 1; k <= nf; ++k) {
+      const uint32_t g = gload + (uint32_t)k;
+      const int st = g % kCombStages, stp = (g - 1) % kCombStages;
+      mbar_wait(&full_bar[st], (g / kCombStages) & 1u);
+      const uint8_t* cur = tiles + st * kCombStageBytes + (run * kCombR) * kCombTW + strip * 8;
+      const uint8_t* prv = tiles + stp * kCombStageBytes + (run * kCombR) * kCombTW + strip * 8;
+      uint32_t vS = 0, vL = 0, vM = 0;
+      if (!edge) {
+        comb_tile_rows<false>(cur, prv, y0 + run * kCombR, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
+      } else if (rows_live) {
+        comb_tile_rows<true>(cur, prv, y0 + run * kCombR, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
+      }
+      vS = __reduce_add_sync(0xFFFFFFFFu, vS);
+      vL = __reduce_add_sync(0xFFFFFFFFu, vL);
+      vM = __reduce_add_sync(0xFFFFFFFFu, vM);
+      const int rb = gstep & 1;
+      if (lane == 0) { atomicAdd(&red[rb][0], vM); atomicAdd(&red[rb][1], vS); atomicAdd(&red[rb][2], vL); }
+      __syncthreads();                               // all reads of stage stp done; red[rb] complete
+      if (tid < 3) {
+        const unsigned v = atomicExch(&red[rb][tid], 0u);          // packed top | bottom<<16
+        int* o = a.counts + (size_t)(seg.fbegin + k - 1 - a.out_frame0) * 12 + P.cls * 6 + tid;
+        if (v & 0xFFFFu) atomicAdd(o, (int)(v & 0xFFFFu));         // top field   [metric]
+        if (v >> 16) atomicAdd(o + 3, (int)(v >> 16));             // bottom field [metric]
+      }
+      if (tid == 0 && (k - 1 + kCombStages) < nloads) issue(k - 1 + kCombStages);
+      ++gstep;
+    }
+    gload += (uint32_t)nloads;
+  }
+}
+
+}  // namespace amtk

@@ -1,0 +1,168 @@
+// scan_kernels.cuh -- LogoScan accumulation and logo erase on the GPU.
+//
+// LogoScan::AddFrame (LogoScan.hpp:594-659): per frame, the ROI border pixels decide whether the background is
+// flat (max-min <= thy on Y, U and V) and give the background level (mean of the middle half of the sorted border
+// values, :414-428); valid frames add f, bg, f^2, bg^2, f*bg to per-pixel accumulators (LogoColor::Add, :357-364).
+// The reference accumulates ints in doubles; every partial sum is an exact integer < 2^53, so exact u64 integer
+// accumulation is bit-identical after conversion.  A 256-bin histogram replaces the sort exactly.
+#pragma once
+#include "amtk_internal.h"
+#include "exact_math.h"
+
+namespace amtk {
+
+struct ScanClip {
+  const uint8_t* base; long long frame_stride; long long offU, offV;
+  int pitchY, pitchUV;
+  int scanx, scany, scanw, scanh, logUVx, logUVy, thy;
+  int frame0, nframes;
+};
+
+// One CTA (256 threads) per frame: border histogram per plane -> {valid, bgY, bgU, bgV}.
+__global__ void __launch_bounds__(256) scan_border_kernel(const ScanClip c, const uint8_t* __restrict__ select,
+                                                          int4* __restrict__ frame_bg) {
+  __shared__ unsigned int hist[3][256];
+  __shared__ int res[3][2];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  if (select && !select[f]) { if (tid == 0) frame_bg[f] = make_int4(0, 0, 0, 0); return; }
+  for (int i = tid; i < 3 * 256; i += 256) (&hist[0][0])[i] = 0u;
+  __syncthreads();
+  const uint8_t* fr = c.base + (long long)(c.frame0 + f) * c.frame_stride;
+  for (int pl = 0; pl < 3; ++pl) {
+    const int w = pl ? (c.scanw >> c.logUVx) : c.scanw, h = pl ? (c.scanh >> c.logUVy) : c.scanh;
+    const int pitch = pl ? c.pitchUV : c.pitchY;
+    const uint8_t* p = fr + (pl == 0 ? 0 : (pl == 1 ? c.offU : c.offV)) +
+                       (pl ? ((c.scanx >> c.logUVx) + (long long)(c.scany >> c.logUVy) * pitch)
+                           : (c.scanx + (long long)c.scany * pitch));
+    // border = rows 0 and h-1 (all x) + columns 0 and w-1 for y in [1,h-1)  (:616-635)
+    const int nb = 2 * w + 2 * (h - 2);
+    for (int i = tid; i < nb; i += 256) {
+      int x, y;
+      if (i < w) { x = i; y = 0; }
+      else if (i < 2 * w) { x = i - w; y = h - 1; }
+      else { const int k = i - 2 * w; y = 1 + (k >> 1); x = (k & 1) ? (w - 1) : 0; }
+      atomicAdd(&hist[pl][p[x + (long long)y * pitch]], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid < 3) {
+    const int pl = tid;
+    const int w = pl ? (c.scanw >> c.logUVx) : c.scanw, h = pl ? (c.scanh >> c.logUVy) : c.scanh;
+    const int n = 2 * w + 2 * (h - 2);
+    const int lo = n / 4, hi = n - n / 4;            // sorted ranks [lo, hi) are averaged (:421-423)
+    int vmin = -1, vmax = 0, rank = 0;
+    long long sum = 0;
+    for (int v = 0; v < 256; ++v) {
+      const int cnt = (int)hist[pl][v];
+      if (cnt) {
+        if (vmin < 0) vmin = v;
+        vmax = v;
+        const int a = max(rank, lo), b = min(rank + cnt, hi);
+        if (b > a) sum += (long long)(b - a) * v;
+        rank += cnt;
+      }
+    }
+    const int nn = hi - lo;
+    res[pl][0] = (vmax - vmin > c.thy) ? 0 : 1;      // abs(front-back) > thy rejects (:639-649)
+    res[pl][1] = (int)((sum + nn / 2) / nn);         // (int)((t + nn/2)/nn) on exact integers (:425-427)
+  }
+  __syncthreads();
+  if (tid == 0) frame_bg[f] = make_int4(res[0][0] & res[1][0] & res[2][0], res[0][1], res[1][1], res[2][1]);
+}
+
+// grid (pixel blocks, frame splits): thread per ROI pixel (Y then U then V), loops over its share of the frames.
+// sums: [npix][3] u64 = sumF, sumF2, sumFB.  plane scalars bgsum[pl*2+{0,1}] = sumB, sumB2; bgsum[6] = nvalid.
+__global__ void __launch_bounds__(256) scan_accumulate_kernel(const ScanClip c, const int4* __restrict__ frame_bg,
+                                                              unsigned long long* __restrict__ sums,
+                                                              unsigned long long* __restrict__ bgsum,
+                                                              uint8_t* __restrict__ valid_out) {
+  const int ny = c.scanw * c.scanh, wc = c.scanw >> c.logUVx, hc = c.scanh >> c.logUVy, nc = wc * hc;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = (c.nframes + gridDim.y - 1) / gridDim.y;
+  const int f_lo = blockIdx.y * per, f_hi = min(c.nframes, f_lo + per);
+  if (i < ny + 2 * nc) {
+    int pl, x, y, pitch; long long off;
+    if (i < ny) { pl = 0; y = i / c.scanw; x = i - y * c.scanw; pitch = c.pitchY; off = c.scanx + (long long)c.scany * pitch; }
+    else {
+      const int k = (i - ny) % nc; pl = 1 + (i - ny) / nc; y = k / wc; x = k - y * wc; pitch = c.pitchUV;
+      off = (pl == 1 ? c.offU : c.offV) + (c.scanx >> c.logUVx) + (long long)(c.scany >> c.logUVy) * pitch;
+    }
+    const uint8_t* p = c.base + (long long)c.frame0 * c.frame_stride + off + x + (long long)y * pitch;
+    unsigned long long sF = 0, sF2 = 0, sFB = 0;
+    for (int f = f_lo; f < f_hi; ++f) {
+      const int4 bg = frame_bg[f];
+      if (bg.x) {
+        const unsigned v = p[(long long)f * c.frame_stride];
+        const unsigned b = (unsigned)(pl == 0 ? bg.y : (pl == 1 ? bg.z : bg.w));
+        sF += v; sF2 += v * v; sFB += v * b;
+      }
+    }
+    if (sF | sF2 | sFB) {
+      atomicAdd(&sums[(size_t)i * 3 + 0], sF); atomicAdd(&sums[(size_t)i * 3 + 1], sF2); atomicAdd(&sums[(size_t)i * 3 + 2], sFB);
+    }
+  }
+  // per-plane background sums + valid count: one thread per frame split
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long sb[3] = { 0, 0, 0 }, sb2[3] = { 0, 0, 0 }, nv = 0;
+    for (int f = f_lo; f < f_hi; ++f) {
+      const int4 bg = frame_bg[f];
+      if (valid_out) valid_out[f] = (uint8_t)bg.x;
+      if (bg.x) {
+        ++nv;
+        sb[0] += bg.y; sb2[0] += (unsigned long long)bg.y * bg.y;
+        sb[1] += bg.z; sb2[1] += (unsigned long long)bg.z * bg.z;
+        sb[2] += bg.w; sb2[2] += (unsigned long long)bg.w * bg.w;
+      }
+    }
+    for (int pl = 0; pl < 3; ++pl) { atomicAdd(&bgsum[pl * 2], sb[pl]); atomicAdd(&bgsum[pl * 2 + 1], sb2[pl]); }
+    atomicAdd(&bgsum[6], nv);
+  }
+}
+
+// ---- AMTEraseLogo::Delogo (LogoScan.hpp:1248-1261) on the Y,U,V ROIs of each frame, in place -------------------
+struct EraseJob {
+  uint8_t* base; long long frame_stride; long long offU, offV;
+  int pitchY, pitchUV;           // ELEMENTS
+  int frame0, nframes;
+  int w, h, logUVx, logUVy, imgx, imgy;
+  const float *aY, *bY, *aU, *bU, *aV, *bV;
+  const float* fades;            // [nframes][2] fadeT, fadeB (device)
+  float maxv;
+};
+
+template <typename pixel_t>
+__global__ void __launch_bounds__(256) erase_logo_kernel(const EraseJob j) {
+  const int f = blockIdx.x;
+  const float fadeT = j.fades[f * 2], fadeB = j.fades[f * 2 + 1];
+  pixel_t* fr = reinterpret_cast<pixel_t*>(j.base + (long long)(j.frame0 + f) * j.frame_stride);
+  const int wc = j.w >> j.logUVx, hc = j.h >> j.logUVy, ny = j.w * j.h, nc = wc * hc;
+  const bool frame_mode = (fadeT == fadeB);          // :1374
+  const int uvparity = ((j.imgy / 2) % 2);           // :1385
+  for (int i = threadIdx.x; i < ny + 2 * nc; i += blockDim.x) {
+    pixel_t* p; float a, b, fade;
+    if (i < ny) {
+      const int y = i / j.w, x = i - y * j.w;
+      p = fr + j.imgx + x + (long long)(j.imgy + y) * j.pitchY;
+      if (!frame_mode && y >= 2 * (j.h / 2)) continue;           // field passes cover h/2 rows each (:1380-1381)
+      a = j.aY[i]; b = j.bY[i];
+      fade = frame_mode ? fadeT : ((y & 1) ? fadeB : fadeT);      // rows of the top field take fadeT (:1380-1381)
+    } else {
+      const int k = (i - ny) % nc, pl = (i - ny) / nc;
+      const int y = k / wc, x = k - y * wc;
+      p = reinterpret_cast<pixel_t*>(reinterpret_cast<uint8_t*>(fr) + (pl == 0 ? j.offU : j.offV)) +
+          (j.imgx >> j.logUVx) + x + (long long)((j.imgy >> j.logUVy) + y) * j.pitchUV;
+      if (!frame_mode && y >= 2 * (hc / 2)) continue;            // hUV/2 rows per field pass (:1391-1395)
+      a = (pl == 0 ? j.aU : j.aV)[k]; b = (pl == 0 ? j.bU : j.bV)[k];
+      // chroma row y belongs to the top-field group when (y & 1) == uvparity (:1385-1396)
+      fade = frame_mode ? fadeT : (((y & 1) == uvparity) ? fadeT : fadeB);
+    }
+    const float srcv = (float)*p;
+    const float tmp = remove_logo(srcv, a, b, j.maxv, fade, AMTK_FSUB(1.0f, fade));
+    const float t = AMTK_FADD(tmp, 0.5f);
+    const float m = (t > 0.0f) ? t : 0.0f;           // std::max(tmp + 0.5f, 0.0f)
+    const float cl = (j.maxv < m) ? j.maxv : m;      // std::min(.., maxv)
+    *p = (pixel_t)cl;
+  }
+}
+
+}  // namespace amtk

@@ -51,10 +51,12 @@ def make_logo(w=64, h=64, seed=1, L8=230):
 
 
 def logo_fade256(n, period=200):
-    """Logo visibility schedule (0..256) per frame index tensor n: off / fade-in(10) / on / fade-out(10) / off."""
+    """Logo visibility schedule (0..256) per frame index tensor n: off for the first quarter of each period,
+    linear fade-in over period/20 frames, on, fade-out ending at 85 % of the period, off."""
     p = n % period
-    up = torch.clamp((p - 50) * 26, 0, 256)
-    down = torch.clamp((170 - p) * 26, 0, 256)
+    ramp = max(1, period // 20)
+    up = torch.clamp(((p - period // 4) * 256) // ramp, 0, 256)
+    down = torch.clamp((((period * 17) // 20 - p) * 256) // ramp, 0, 256)
     return torch.minimum(up, down)
 
 

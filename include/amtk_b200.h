@@ -1,0 +1,178 @@
+/* include/amtk_b200.h -- C ABI of libamtk_b200.so: the B200-native (sm_100a) implementation of Amatsukaze's
+ * per-frame pixel-analysis hot path (logo-template correlation, LogoScan accumulation, logo erase, and the
+ * field-difference / combing metric).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference's Amatsukaze/ directory).  A reference-side
+ * binding (what a maintainer would add to LogoScan.hpp / FilteredSource.hpp) is shown in INTEGRATION.md.
+ *
+ * Conventions (mirroring the reference's C exports, StreamUtils.hpp:1037-1039 + LogoScan.hpp:1083-1098):
+ *   - every function returns 1 on success, 0 on failure; after a failure amtk_last_error() returns the
+ *     message for the calling thread (the reference: `return false` after ctx->setError(); text fetched with
+ *     AMTContext_GetError()).
+ *   - handles are opaque, owned by the caller, released with the matching *_destroy().
+ *   - a context is bound to ONE CUDA device and ONE stream; calls on distinct contexts may run concurrently
+ *     (the reference filters answer CACHE_GET_MTMODE with MT_NICE_FILTER, LogoScan.hpp:1220-1225,1500-1505).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef AMTK_B200_H
+#define AMTK_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMTK_API __attribute__((visibility("default")))
+
+typedef struct amtk_ctx amtk_ctx;
+typedef struct amtk_logo amtk_logo;
+typedef struct amtk_scan amtk_scan;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context / errors   (replaces AMTContext_Create / ATMContext_Delete / AMTContext_GetError,
+ *                     StreamUtils.hpp:1037-1039, for this path)
+ * ------------------------------------------------------------------------------------------- */
+AMTK_API const char* amtk_last_error(void);
+AMTK_API int amtk_version(void);
+/* number of CUDA devices visible (0 when there is no driver/GPU; never fails) */
+AMTK_API int amtk_device_count(void);
+/* device: CUDA ordinal.  stream: the cudaStream_t every kernel of this context is launched on (e.g. torch's
+ * current stream); NULL = the legacy default stream. */
+AMTK_API int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out);
+AMTK_API void amtk_ctx_destroy(amtk_ctx* ctx);
+AMTK_API int amtk_ctx_synchronize(amtk_ctx* ctx);
+/* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
+AMTK_API int64_t amtk_ctx_launch_count(const amtk_ctx* ctx);
+
+/* Pinned host memory for the host-buffer entry points (optional; pageable memory works, only slower). */
+AMTK_API int amtk_host_alloc(size_t bytes, void** out);
+AMTK_API void amtk_host_free(void* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Clip descriptor: a run of planar YUV frames, either resident in HBM or in host memory.
+ * Describes what the reference's filters read through PVideoFrame::GetReadPtr/GetPitch(PLANAR_Y|U|V)
+ * (LogoScan.hpp:1138-1145, AMTSource.hpp:357-408).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct amtk_clip {
+  const void* base;        /* first byte of frame 0 (its Y plane)                                  */
+  int64_t frame_stride;    /* bytes from one frame to the next (multiple of 16)                    */
+  int64_t off_u, off_v;    /* byte offsets of the U and V planes inside a frame (multiples of 16)  */
+  int32_t width, height;   /* luma size in pixels                                                  */
+  int32_t pitch_y, pitch_uv; /* bytes per row (multiples of 16)                                    */
+  int32_t log_uvx, log_uvy;  /* chroma subsampling shifts (1,1 for YV12 / YUV420P10)               */
+  int32_t bytes_per_sample;  /* 1 (YV12) or 2 (YUV420P10/P12/P16, little endian)                   */
+  int32_t bits_per_sample;   /* 8, 10, 12 or 16: maxv = (1<<bits)-1 (LogoScan.hpp:1130,1575)       */
+  int32_t num_frames;
+  int32_t on_device;         /* 1: base is a device pointer on the context's device; 0: host pointer */
+} amtk_clip;
+
+/* ---------------------------------------------------------------------------------------------
+ * Logos   (replaces logo::LogoData / logo::LogoDataParam, AMTLogo.hpp:49-280, LogoScan.hpp:61-334)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct amtk_logo_info {
+  int32_t w, h, log_uvx, log_uvy;
+  int32_t imgw, imgh, imgx, imgy;
+  int32_t maskpixels;      /* min(w*h,(int)(w*h*maskratio)), LogoScan.hpp:172; 0 before create_mask */
+  int32_t count;           /* mask pixels the y,x in [2,dim-2) scan visits (= kernels/scales rows)   */
+  float black_score;       /* LogoScan.hpp:227-228                                                   */
+} amtk_logo_info;
+
+/* data: aY,bY,aU,bU,aV,bV contiguous floats -- LogoData's own layout (AMTLogo.hpp:203-212).
+ * Logos are host objects: ctx may be NULL; the HBM copy of a logo's tables is made by the first context that
+ * evaluates it (and the logo then belongs to that device). */
+AMTK_API int amtk_logo_create(amtk_ctx* ctx, const float* data, int w, int h, int log_uvx, int log_uvy,
+                              int imgw, int imgh, int imgx, int imgy, amtk_logo** out);
+/* LogoData::Load (AMTLogo.hpp:257-279): reads a .lgd, skipping the AviUtl base part; header540 (may be NULL)
+ * receives the raw 540-byte LogoHeader (AMTLogo.hpp:19-47). */
+AMTK_API int amtk_logo_load(amtk_ctx* ctx, const char* path, amtk_logo** out, void* header540);
+/* LogoData::Save (AMTLogo.hpp:239-255) incl. the AviUtl-compatible base part (ToOutLGP, :96-167). */
+AMTK_API int amtk_logo_save(const amtk_logo* logo, const char* path, const char* name, int service_id);
+AMTK_API void amtk_logo_destroy(amtk_logo* logo);
+/* DeintLogo (LogoScan.hpp:734-761): vertical [1 2 1]/4 of the Y planes, same image placement. */
+AMTK_API int amtk_logo_deint(const amtk_logo* src, amtk_logo** out);
+/* LogoDataParam::MakeFieldLogo (LogoScan.hpp:257-283). */
+AMTK_API int amtk_logo_field(const amtk_logo* src, int bottom, amtk_logo** out);
+/* LogoDataParam::CreateLogoMask (LogoScan.hpp:112-229): mask, kernels, scale tables, blackScore; uploads the
+ * evaluation tables to HBM on next use.  Must be called before the logo is used by scan/analyze entry points.
+ * (Setup-time host code, once per logo -- exactly where the reference runs it; the per-frame path is CUDA.) */
+AMTK_API int amtk_logo_create_mask(amtk_logo* logo, float maskratio);
+AMTK_API int amtk_logo_get_info(const amtk_logo* logo, amtk_logo_info* out);
+/* Copies out host tables (any pointer may be NULL): data (LogoData layout), mask w*h, kernels count*25,
+ * scales count*32*2 {scale,scale2}. */
+AMTK_API int amtk_logo_get_tables(const amtk_logo* logo, float* data, uint8_t* mask, float* kernels, float* scales);
+
+/* ---------------------------------------------------------------------------------------------
+ * Logo evaluation
+ * ------------------------------------------------------------------------------------------- */
+/* LogoFrame::ScanFrame over frames [frame0, frame0+nframes) (LogoScan.hpp:1543-1589; the CMAnalyze entry,
+ * CMAnalyze.hpp:291-292).  logos[i] are DEINT logos with masks.  out: float[nframes][nlogos][2] = corr0,corr1
+ * (EvalResult, :1532-1535); a logo whose imgw/imgh differ from the clip yields (0,-1) (:1551-1558).
+ * pitch_elems_override: 0 = use clip.pitch_y/bytes_per_sample; >0 = element pitch to use for addressing the Y
+ * plane (the reference passes the BYTE pitch even for 16-bit samples, :1547,1561 -- see INTEGRATION.md).
+ * out_on_device: 1 = out is a device pointer (stays in HBM), 0 = host pointer. */
+AMTK_API int amtk_logo_scan_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
+                                   int frame0, int nframes, int pitch_elems_override, float* out, int out_on_device);
+/* AMTAnalyzeLogo::GetFrameT body per SOURCE frame (LogoScan.hpp:1119-1161): out float[nframes][33] =
+ * LogoAnalyzeFrame{p[11],t[11],b[11]} (:1100-1103) for source frames frame0.. (the caller groups 8 per output
+ * frame and clamps, :1133). */
+AMTK_API int amtk_logo_analyze_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* deint_logo,
+                                      const amtk_logo* field_top, const amtk_logo* field_bottom,
+                                      int frame0, int nframes, float* out, int out_on_device);
+/* General form used by LogoAnalyzer::ReMakeLogo's 20-fade sweep (LogoScan.hpp:955-975): evaluates
+ * EvaluateLogo(DeintY(roi), maxv, fades[i]) for every frame; out float[nframes][nfades] (signed scores). */
+AMTK_API int amtk_logo_eval_fades(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* deint_logo,
+                                  const float* fades, int nfades, int frame0, int nframes, float* out, int out_on_device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Field-difference / combing metric (the telecine pre-pass the reference drives through
+ * AMTFilterSource::FilterPass/ReadAllFrames, FilteredSource.hpp:232-238,417-439,519-544, and computes in the
+ * external KFM plugin).  Integer spec: DESIGN.md section 4.
+ * counts int32[nframes][12] = [plane class Y,C][field top,bottom][move, shima, lshima].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct amtk_comb_params {
+  int32_t th_move_y, th_shima_y, th_lshima_y;   /* defaults 20, 12, 36 */
+  int32_t th_move_c, th_shima_c, th_lshima_c;   /* defaults 24, 16, 48 */
+} amtk_comb_params;
+AMTK_API void amtk_comb_default_params(amtk_comb_params* p);
+/* prev(frame0) is frame0-1 when frame0 > 0 (halo frame for range-sharded clips), else frame0 itself. */
+AMTK_API int amtk_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_comb_params* params,
+                              int frame0, int nframes, int32_t* counts, int out_on_device);
+
+/* The fused hot-path step of BASELINE.json's headline metric: one pass over frames [frame0, frame0+nframes)
+ * producing BOTH the ScanFrame scores (as amtk_logo_scan_frames) and the combing counters (as amtk_comb_frames). */
+AMTK_API int amtk_scan_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
+                                   const amtk_comb_params* params, int frame0, int nframes,
+                                   float* scores, int32_t* counts, int out_on_device);
+
+/* ---------------------------------------------------------------------------------------------
+ * LogoScan accumulation (replaces logo::LogoScan, LogoScan.hpp:398-660; the ScanLogo C export's inner loop,
+ * :1083-1098 -> :881-914)
+ * ------------------------------------------------------------------------------------------- */
+AMTK_API int amtk_scan_create(amtk_ctx* ctx, int scanw, int scanh, int log_uvx, int log_uvy, int thy, amtk_scan** out);
+AMTK_API void amtk_scan_destroy(amtk_scan* s);
+/* LogoScan::AddFrame for every frame in [frame0, frame0+nframes) with the ROI at (scanx, scany) (:594-659);
+ * valid_out (may be NULL; host pointer) receives 1/0 per frame = AddFrame's return value.
+ * frame_select (may be NULL; host pointer, nframes bytes): only frames with a non-zero byte are offered
+ * (ReMakeLogo's `minFades[i] > 8` filter, :1018-1021). */
+AMTK_API int amtk_scan_add_frames(amtk_scan* s, const amtk_clip* clip, int scanx, int scany, int frame0, int nframes,
+                                  const uint8_t* frame_select, uint8_t* valid_out);
+AMTK_API int amtk_scan_num_valid(const amtk_scan* s);
+/* raw accumulators as doubles, plane-major Y,U,V, 5 per pixel {sumF,sumB,sumF2,sumB2,sumFB} (LogoColor, :346) */
+AMTK_API int amtk_scan_get_sums(amtk_scan* s, double* out);
+/* LogoScan::Normalize(maxv) + GetLogo(clean) (:471-566): fills data (LogoData layout); returns 0 with error
+ * "Insufficient logo frames" when the reference would return nullptr (:847-849). */
+AMTK_API int amtk_scan_get_logo(amtk_scan* s, int maxv, int clean, float* data);
+
+/* ---------------------------------------------------------------------------------------------
+ * Logo erase (replaces AMTEraseLogo::Delogo on Y,U,V, LogoScan.hpp:1248-1261,1374-1397), in place on a
+ * device-resident or host clip.  fades float[nframes][2] = fadeT,fadeB per frame (host pointer).
+ * ------------------------------------------------------------------------------------------- */
+AMTK_API int amtk_erase_logo_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* logo,
+                                    int frame0, int nframes, const float* fades);
+/* AMTEraseLogo::CalcFade2 (LogoScan.hpp:1263-1315) on host records (float[num_records][33]). */
+AMTK_API void amtk_calc_fade2(const float* records, int num_records, int num_frames, int n, float* fade_t, float* fade_b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMTK_B200_H */
