@@ -52,6 +52,8 @@ SIGNATURES = [
     ("amtk_ctx_destroy", None, [V]),
     ("amtk_ctx_synchronize", C.c_int, [V]),
     ("amtk_ctx_launch_count", C.c_int64, [V]),
+    ("amtk_ctx_set_kernel_timing", C.c_int, [V, C.c_int]),
+    ("amtk_ctx_get_kernel_timing", C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     ("amtk_host_alloc", C.c_int, [C.c_size_t, VP]),
     ("amtk_host_free", None, [V]),
     ("amtk_logo_create", C.c_int, [V, c_float_p] + [C.c_int] * 8 + [VP]),
@@ -164,6 +166,15 @@ class Context:
     @property
     def launches(self):
         return int(self.L.amtk_ctx_launch_count(self.h))
+
+    def set_kernel_timing(self, enable):
+        check(self.L.amtk_ctx_set_kernel_timing(self.h, int(enable)))
+
+    def kernel_timing(self, reset=True):
+        """(total ms, launches) of the comb kernel since the last reset, from CUDA events on the launch stream."""
+        ms, n = C.c_double(), C.c_int64()
+        check(self.L.amtk_ctx_get_kernel_timing(self.h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
 
     # ---- logos (host objects; uploaded to this context's device on first use) ----
     def logo(self, data, w, h, imgw, imgh, imgx, imgy, log_uvx=1, log_uvy=1):

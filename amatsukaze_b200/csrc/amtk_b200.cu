@@ -6,6 +6,7 @@
 #include "comb_kernels.cuh"
 #include "scan_kernels.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -182,6 +183,37 @@ static int comb_thresholds_ok(const amtk_comb_params* p) {
   return 1;
 }
 
+// Everything the host needs to know about one compiled comb-kernel variant.
+struct CombVariant {
+  int R, strip, stages, TH, boxH, threads, smem;
+  void (*kernel)(const CombArgs);
+};
+template <typename Cfg> static CombVariant make_variant() {
+  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_u8_kernel<Cfg> };
+}
+static const CombVariant* comb_variants(int* n) {
+  static const CombVariant v[] = {
+    make_variant<CombCfg<15, 8, 4>>(), make_variant<CombCfg<16, 8, 4>>(), make_variant<CombCfg<17, 8, 4>>(),
+    make_variant<CombCfg<15, 8, 3>>(), make_variant<CombCfg<16, 8, 3>>(), make_variant<CombCfg<17, 8, 3>>(),
+    make_variant<CombCfg<15, 4, 4>>(), make_variant<CombCfg<16, 4, 4>>(), make_variant<CombCfg<17, 4, 4>>(),
+    make_variant<CombCfg<15, 4, 3>>(), make_variant<CombCfg<16, 4, 3>>(), make_variant<CombCfg<17, 4, 3>>(),
+  };
+  *n = (int)(sizeof(v) / sizeof(v[0]));
+  return v;
+}
+static int g_comb_strip = 8, g_comb_stages = 4, g_comb_R = 0, g_comb_ctas_per_sm = 0;   // tuning knobs (env AMTK_COMB_*)
+
+// rows per run: the R in {15,16,17} that wastes the fewest rows over luma + chroma (1080/540 -> 17, 720/360 -> 15)
+static int pick_comb_R(int hY, int hC) {
+  int best = 16; long long best_waste = -1;
+  for (int R = 17; R >= 15; --R) {
+    const int th = kCombRuns * R;
+    const long long waste = (long long)((hY + th - 1) / th) * th - hY + 2LL * (((hC + th - 1) / th) * th - hC) / 2;
+    if (best_waste < 0 || waste < best_waste) { best_waste = waste; best = R; }
+  }
+  return best;
+}
+
 static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi,
                        const amtk_comb_params* prm, int* dcounts, int out_row0) {
   if (clip->bytes_per_sample != 1) AMTK_FAIL("comb: 16-bit samples are not supported by this build (YV12 only)");
@@ -189,14 +221,19 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
       (reinterpret_cast<uintptr_t>(win.dev_base) & 15))
     AMTK_FAIL("comb: base, frame_stride, plane offsets and pitches must be multiples of 16 bytes (TMA)");
   if (!ctx->encode_tiled) AMTK_FAIL("cuTensorMapEncodeTiled unavailable (driver too old?)");
+  const int hY = clip->height, hC = clip->height >> clip->log_uvy;
+  const int R = g_comb_R ? g_comb_R : pick_comb_R(hY, hC);
+  int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
+  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == g_comb_strip && vars[i].stages == g_comb_stages) V = &vars[i];
+  if (!V) AMTK_FAIL("comb: no kernel variant for the requested AMTK_COMB_* settings");
   CombArgs args;
   memset(&args, 0, sizeof(args));
   int tile0 = 0;
   for (int pl = 0; pl < 3; ++pl) {
     CombPlane& P = args.plane[pl];
     P.W = pl ? (clip->width >> clip->log_uvx) : clip->width;
-    P.H = pl ? (clip->height >> clip->log_uvy) : clip->height;
-    P.tilesX = (P.W + kCombTW - 1) / kCombTW; P.tilesY = (P.H + kCombTH - 1) / kCombTH;
+    P.H = pl ? hC : hY;
+    P.tilesX = (P.W + kCombTW - 1) / kCombTW; P.tilesY = (P.H + V->TH - 1) / V->TH;
     P.tile0 = tile0; tile0 += P.tilesX * P.tilesY;
     P.cls = pl ? 1 : 0;
     const int thM = pl ? prm->th_move_c : prm->th_move_y;
@@ -208,7 +245,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     const int pitch = pl ? clip->pitch_uv : clip->pitch_y;
     cuuint64_t gdim[3] = { (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)win.count };
     cuuint64_t gstr[2] = { (cuuint64_t)pitch, (cuuint64_t)clip->frame_stride };
-    cuuint32_t box[3] = { (cuuint32_t)kCombTW, (cuuint32_t)kCombBoxH, 1u };
+    cuuint32_t box[3] = { (cuuint32_t)kCombTW, (cuuint32_t)V->boxH, 1u };
     cuuint32_t estr[3] = { 1u, 1u, 1u };
     CUresult r = ctx->encode_tiled(&args.map[pl], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                                    const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
@@ -218,46 +255,30 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   }
   const int ntiles = tile0;
   const int nf = hi - lo;
-  // ---- static weighted partition of (tile, frame) pairs over the resident CTAs ----
+  // ---- static partition of (tile, frame) pairs over the resident CTAs: tile-major, frame-minor, equal shares.
+  // A tile-frame costs the same wherever it lies (the kernel is issue/latency bound per warp, and tile shapes are
+  // chosen so that bands are full), so equal counts = equal time; each CTA touches at most ~2 tiles.
   int occ = 0;
-  AMTK_CUDA(cudaFuncSetAttribute(comb_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombSmemBytes));
-  AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, comb_u8_kernel, kCombThreads, kCombSmemBytes));
+  AMTK_CUDA(cudaFuncSetAttribute(V->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
+  AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, V->kernel, V->threads, V->smem));
   if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
-  std::vector<long long> wt((size_t)ntiles);
-  long long total = 0;
-  for (int pl = 0; pl < 3; ++pl) {
-    const CombPlane& P = args.plane[pl];
-    for (int ty = 0; ty < P.tilesY; ++ty)
-      for (int tx = 0; tx < P.tilesX; ++tx) {
-        // cost model: live 16-row runs x 128-byte rows (a partially covered tile still computes whole runs);
-        // a constant per tile-frame stands for the barrier/reduction overhead
-        const int rows = std::min(kCombTH, P.H - ty * kCombTH);
-        const int runs = (rows + kCombR - 1) / kCombR;
-        const long long c = (long long)runs * kCombR * kCombTW + 2048;
-        wt[P.tile0 + ty * P.tilesX + tx] = c;
-        total += c * nf;
-      }
-  }
-  const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (long long)ntiles * nf);
+  if (g_comb_ctas_per_sm > 0) occ = std::min(occ, g_comb_ctas_per_sm);
+  const long long total = (long long)ntiles * nf;
+  const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, total);
   std::vector<CombSegment> segs;
   std::vector<int> seg_start((size_t)grid + 1, 0);
-  {
-    int b = 0; long long acc = 0;                       // acc = weight handed to CTAs [0,b] so far
-    long long target = (total * (b + 1)) / grid;
-    for (int t = 0; t < ntiles; ++t) {
-      int f = 0;
-      while (f < nf) {
-        // how many frames of this tile still fit into CTA b's share
-        long long room = target - acc;
-        int take = (int)std::min<long long>(nf - f, std::max<long long>(1, (room + wt[t] / 2) / wt[t]));
-        if (b == grid - 1) take = nf - f;
-        segs.push_back(CombSegment{ t, lo - win.first + f, lo - win.first + f + take });
-        acc += wt[t] * take; f += take;
-        while (b < grid - 1 && acc >= target) { ++b; seg_start[b] = (int)segs.size(); target = (total * (b + 1)) / grid; }
-      }
+  for (int b = 0; b < grid; ++b) {
+    const long long lo_i = total * b / grid, hi_i = total * (b + 1) / grid;     // [lo_i, hi_i) of the tile-major order
+    seg_start[b] = (int)segs.size();
+    long long i = lo_i;
+    while (i < hi_i) {
+      const int t = (int)(i / nf), f = (int)(i % nf);
+      const int take = (int)std::min<long long>(nf - f, hi_i - i);
+      segs.push_back(CombSegment{ t, lo - win.first + f, lo - win.first + f + take });
+      i += take;
     }
-    for (int i = b + 1; i <= grid; ++i) seg_start[i] = (int)segs.size();
   }
+  seg_start[grid] = (int)segs.size();
   const size_t seg_bytes = segs.size() * sizeof(CombSegment), st_bytes = seg_start.size() * sizeof(int);
   const size_t st_off = (seg_bytes + 255) & ~(size_t)255;
   if (!ensure(&ctx->small, &ctx->small_bytes, st_off + st_bytes)) return 0;
@@ -269,8 +290,15 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   args.counts = dcounts;
   args.out_frame0 = out_row0 - win.first;
   AMTK_CUDA(cudaMemsetAsync(dcounts + (size_t)(lo - out_row0) * 12, 0, (size_t)nf * 12 * sizeof(int), ctx->stream));
-  comb_u8_kernel<<<grid, kCombThreads, kCombSmemBytes, ctx->stream>>>(args);
+  std::pair<cudaEvent_t, cudaEvent_t> ev{ nullptr, nullptr };
+  if (ctx->timing) {
+    if (!ctx->timing_pool.empty()) { ev = ctx->timing_pool.back(); ctx->timing_pool.pop_back(); }
+    else { AMTK_CUDA(cudaEventCreate(&ev.first)); AMTK_CUDA(cudaEventCreate(&ev.second)); }
+    AMTK_CUDA(cudaEventRecord(ev.first, ctx->stream));
+  }
+  V->kernel<<<grid, V->threads, V->smem, ctx->stream>>>(args);
   AMTK_CUDA(cudaGetLastError());
+  if (ctx->timing) { AMTK_CUDA(cudaEventRecord(ev.second, ctx->stream)); ctx->timing_events.push_back(ev); }
   ctx->launches += 1;
   return 1;
 }
@@ -322,6 +350,11 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
     else cudaGetLastError();
   });
   c->encode_tiled = g_encode;
+  // tuning knobs for the comb kernel variant (defaults are the measured best)
+  if (const char* e = getenv("AMTK_COMB_STRIP")) g_comb_strip = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_STAGES")) g_comb_stages = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_R")) g_comb_R = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_CTAS")) g_comb_ctas_per_sm = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }
   *out = c;
@@ -338,6 +371,7 @@ void amtk_ctx_destroy(amtk_ctx* c) {
   if (c->small) cudaFree(c->small);
   if (c->dout) cudaFree(c->dout);
   if (c->dout2) cudaFree(c->dout2);
+  for (auto* v : { &c->timing_events, &c->timing_pool }) for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   cudaSetDevice(prev);
   delete c;
@@ -350,6 +384,29 @@ int amtk_ctx_synchronize(amtk_ctx* c) {
   return 1;
 }
 int64_t amtk_ctx_launch_count(const amtk_ctx* c) { return c ? c->launches : 0; }
+
+int amtk_ctx_set_kernel_timing(amtk_ctx* c, int enable) {
+  if (!c) AMTK_FAIL("null context");
+  c->timing = enable != 0;
+  return 1;
+}
+
+int amtk_ctx_get_kernel_timing(amtk_ctx* c, double* ms_total, int64_t* launches, int reset) {
+  if (!c) AMTK_FAIL("null context");
+  DevSelect ds(c); if (!ds.ok) return 0;
+  AMTK_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& ev : c->timing_events) {
+    float ms = 0.0f;
+    AMTK_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    c->timing_ms += ms; c->timing_count += 1;
+    c->timing_pool.push_back(ev);
+  }
+  c->timing_events.clear();
+  if (ms_total) *ms_total = c->timing_ms;
+  if (launches) *launches = c->timing_count;
+  if (reset) { c->timing_ms = 0.0; c->timing_count = 0; }
+  return 1;
+}
 
 int amtk_host_alloc(size_t bytes, void** out) {
   if (!out) AMTK_FAIL("amtk_host_alloc: out is null");

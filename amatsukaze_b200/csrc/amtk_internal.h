@@ -59,6 +59,11 @@ struct amtk_ctx {
   void* dout = nullptr; size_t dout_bytes = 0;             // device-side outputs when the caller's are on the host
   void* dout2 = nullptr; size_t dout2_bytes = 0;
   amtk_encode_tiled_fn encode_tiled = nullptr;
+  // optional per-launch timing of the dominant (comb) kernel with CUDA events on the launching stream
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;   // recorded, not yet resolved
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_pool;     // free pairs
+  double timing_ms = 0.0; int64_t timing_count = 0;
 };
 
 struct amtk_logo {

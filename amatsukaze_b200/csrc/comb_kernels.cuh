@@ -7,12 +7,13 @@
 //   per frame: int32[12] = [Y, C(=U+V)] x [top, bottom] x [move, shima, lshima]
 //
 // Design for sm_100a:
-//   * work unit = (plane tile of 128 px x 128 rows, run of consecutive frames).  A CTA streams the tile of frame
-//     n, n+1, ... through a 4-stage shared-memory ring filled by TMA (cp.async.bulk.tensor.3d, one instruction
+//   * work unit = (plane tile of 128 px x 8R rows (R = 15..17 picked so that tiles cover the plane without partial
+//     bands: 1080 = 8 x 136 - 8), run of consecutive frames).  A CTA streams the tile of frame
+//     n, n+1, ... through a 3-4 stage shared-memory ring filled by TMA (cp.async.bulk.tensor.3d, one instruction
 //     per tile incl. the +-2 row halo, out-of-frame rows/cols zero-filled by the TMA unit).  The tile of frame
 //     n-1 is still in the ring when frame n is processed, so the inter-frame difference costs no second HBM read:
-//     every frame byte is fetched from HBM once (plus 4/128 halo rows).
-//   * each thread owns an 8-pixel-wide column strip and walks 16 rows with a 5-row sliding window held in
+//     every frame byte is fetched from HBM once (plus 4/136 halo rows).
+//   * each thread owns a 4- or 8-pixel-wide column strip and walks R rows with a 5-row sliding window held in
 //     registers as fp16x2.  Bytes zero-extended into 16-bit lanes ARE exact fp16 values (subnormals, k*2^-24),
 //     so PRMT is the whole u8->f16 conversion, the 5-tap response (|.| <= 1530 < 2048) is exact in fp16, and
 //     HSET2.GE with |x| does the threshold on two pixels per instruction.  The inter-frame difference runs
@@ -27,14 +28,20 @@
 namespace amtk {
 
 constexpr int kCombTW = 128;            // tile width in bytes (= pixels for u8)
-constexpr int kCombTH = 128;            // tile height (output rows)
-constexpr int kCombR = 16;              // rows per thread run
-constexpr int kCombRuns = kCombTH / kCombR;   // 8
-constexpr int kCombThreads = (kCombTW / 8) * kCombRuns;   // 16 strips x 8 runs = 128
-constexpr int kCombBoxH = kCombTH + 4;  // with +-2 halo rows
-constexpr int kCombStageBytes = kCombTW * kCombBoxH;      // 16896
-constexpr int kCombStages = 4;
-constexpr int kCombSmemBytes = kCombStages * kCombStageBytes + 128;   // + alignment slack
+constexpr int kCombRuns = 8;            // vertical runs per tile (one per half-warp / warp)
+
+// Compile-time shape of one kernel variant: R rows per run (tile height 8R), STRIP pixels per thread-row,
+// STAGES ring slots.
+template <int R_, int STRIP_, int STAGES_>
+struct CombCfg {
+  static constexpr int R = R_, STRIP = STRIP_, STAGES = STAGES_;
+  static constexpr int TH = kCombRuns * R;                 // output rows per tile
+  static constexpr int BOXH = TH + 4;                      // with +-2 halo rows
+  static constexpr int STAGE_BYTES = kCombTW * BOXH;
+  static constexpr int THREADS = (kCombTW / STRIP) * kCombRuns;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 128;  // + alignment slack
+  static constexpr int NQ = STRIP / 2;                     // half2 per thread-row
+};
 
 struct CombPlane {
   int W, H;                 // plane size in pixels
@@ -90,14 +97,29 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 // ---------------------------------------------------------------------------------------------------------
 // per-thread tile-frame body
 // ---------------------------------------------------------------------------------------------------------
-struct H4 { __half2 v[4]; };    // 8 pixels of one row as fp16x2
+template <int NQ> struct HRow { __half2 v[NQ]; };    // STRIP pixels of one row as fp16x2
 
-__device__ __forceinline__ H4 bytes_to_h4(uint2 raw) {
-  H4 r;
-  uint32_t a = __byte_perm(raw.x, 0, 0x4140), b = __byte_perm(raw.x, 0, 0x4342);
-  uint32_t c = __byte_perm(raw.y, 0, 0x4140), d = __byte_perm(raw.y, 0, 0x4342);
-  r.v[0] = *reinterpret_cast<__half2*>(&a); r.v[1] = *reinterpret_cast<__half2*>(&b);
-  r.v[2] = *reinterpret_cast<__half2*>(&c); r.v[3] = *reinterpret_cast<__half2*>(&d);
+template <int STRIP> struct RawRow;
+template <> struct RawRow<8> {
+  uint2 r;
+  __device__ __forceinline__ void load(const uint8_t* p) { r = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ uint32_t word(int i) const { return i ? r.y : r.x; }
+};
+template <> struct RawRow<4> {
+  uint32_t r;
+  __device__ __forceinline__ void load(const uint8_t* p) { r = *reinterpret_cast<const uint32_t*>(p); }
+  __device__ __forceinline__ uint32_t word(int) const { return r; }
+};
+
+template <int STRIP>
+__device__ __forceinline__ HRow<STRIP / 2> bytes_to_half(const RawRow<STRIP>& raw) {
+  HRow<STRIP / 2> r;
+#pragma unroll
+  for (int i = 0; i < STRIP / 4; ++i) {
+    const uint32_t w = raw.word(i);
+    uint32_t a = __byte_perm(w, 0, 0x4140), b = __byte_perm(w, 0, 0x4342);   // zero-extended bytes = exact fp16 subnormals
+    r.v[2 * i] = *reinterpret_cast<__half2*>(&a); r.v[2 * i + 1] = *reinterpret_cast<__half2*>(&b);
+  }
   return r;
 }
 
@@ -106,73 +128,83 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t d, uint32_t kM) {
   return (((d & 0x7F7F7F7Fu) + kM) | d) & 0x80808080u;
 }
 
-template <bool EDGE>
+template <typename Cfg, bool EDGE>
 __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
                                                int y_first /* global y of this thread's first row */, int H,
                                                uint32_t kM, uint32_t thS_bits, uint32_t thL_bits,
                                                uint32_t& oS, uint32_t& oL, uint32_t& oM) {
   // cur/prev point at this thread's strip in smem row (run*R) of the box, i.e. global row y_first-2.
+  constexpr int R = Cfg::R, NQ = Cfg::NQ, STRIP = Cfg::STRIP;
   const __half2 thS = *reinterpret_cast<const __half2*>(&thS_bits);
   const __half2 thL = *reinterpret_cast<const __half2*>(&thL_bits);
   const __half2 k4 = __float2half2_rn(4.0f), km3 = __float2half2_rn(-3.0f);
   uint32_t accS[2] = { 0u, 0u }, accL[2] = { 0u, 0u }, accM[2] = { 0u, 0u };
 
-  uint2 raw_c = *reinterpret_cast<const uint2*>(cur + 2 * kCombTW);      // centre row of j=0
-  uint2 raw_n = *reinterpret_cast<const uint2*>(cur + 3 * kCombTW);
-  H4 h0 = bytes_to_h4(*reinterpret_cast<const uint2*>(cur));
-  H4 h1 = bytes_to_h4(*reinterpret_cast<const uint2*>(cur + kCombTW));
-  H4 h2 = bytes_to_h4(raw_c);
-  H4 h3 = bytes_to_h4(raw_n);
+  RawRow<STRIP> raw_c, raw_n, rtmp;
+  rtmp.load(cur);                 HRow<NQ> h0 = bytes_to_half<STRIP>(rtmp);
+  rtmp.load(cur + kCombTW);       HRow<NQ> h1 = bytes_to_half<STRIP>(rtmp);
+  raw_c.load(cur + 2 * kCombTW);  HRow<NQ> h2 = bytes_to_half<STRIP>(raw_c);     // centre row of j=0
+  raw_n.load(cur + 3 * kCombTW);  HRow<NQ> h3 = bytes_to_half<STRIP>(raw_n);
 #pragma unroll
-  for (int j = 0; j < kCombR; ++j) {
-    const uint2 raw_nn = *reinterpret_cast<const uint2*>(cur + (j + 4) * kCombTW);
-    const H4 h4 = bytes_to_h4(raw_nn);
-    const uint2 pv = *reinterpret_cast<const uint2*>(prev + (j + 2) * kCombTW);
-    const int f = j & 1;       // tile origin and run origin are even => field parity of the row is j&1
+  for (int j = 0; j < R; ++j) {
+    RawRow<STRIP> raw_nn; raw_nn.load(cur + (j + 4) * kCombTW);
+    const HRow<NQ> h4 = bytes_to_half<STRIP>(raw_nn);
+    RawRow<STRIP> pv; pv.load(prev + (j + 2) * kCombTW);
+    const int f = j & 1;          // accumulator slot; mapped to the field parity after the loop
     __half2 tS = thS, tL = thL;
     if (EDGE) {
       const int y = y_first + j;
       if (y < 2 || y >= H - 2) { const uint32_t inf2 = 0x7C007C00u; tS = *reinterpret_cast<const __half2*>(&inf2); tL = tS; }
     }
-    uint32_t mS[4], mL[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      __half2 t = __hadd2(h0.v[q], h4.v[q]);
-      t = __hfma2(k4, h2.v[q], t);
-      const __half2 u = __hadd2(h1.v[q], h3.v[q]);
-      const __half2 r = __habs2(__hfma2(km3, u, t));
-      mS[q] = __hge2_mask(r, tS);
-      mL[q] = __hge2_mask(r, tL);
+    for (int q = 0; q < NQ; q += 2) {
+      uint32_t mS[2], mL[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        __half2 t = __hadd2(h0.v[q + e], h4.v[q + e]);
+        t = __hfma2(k4, h2.v[q + e], t);
+        const __half2 u = __hadd2(h1.v[q + e], h3.v[q + e]);
+        const __half2 r = __habs2(__hfma2(km3, u, t));
+        mS[e] = __hge2_mask(r, tS);
+        mL[e] = __hge2_mask(r, tL);
+      }
+      // 0xFFFF-per-lane masks are subtracted as plain 32-bit integers; decode_pair() undoes the lane coupling
+      accS[f] = accS[f] - mS[0] - mS[1];
+      accL[f] = accL[f] - mL[0] - mL[1];
     }
-    // 0xFFFF-per-lane masks are subtracted as plain 32-bit integers; decode_pair() undoes the lane coupling
-    accS[f] = accS[f] - mS[0] - mS[1]; accS[f] = accS[f] - mS[2] - mS[3];
-    accL[f] = accL[f] - mL[0] - mL[1]; accL[f] = accL[f] - mL[2] - mL[3];
     // inter-frame difference of the centre row, 4 pixels per op
-    const uint32_t d0 = __vabsdiffu4(raw_c.x, pv.x), d1 = __vabsdiffu4(raw_c.y, pv.y);
-    accM[f] = __dp4a(bytes_ge(d0, kM), 0x01010101u, accM[f]);
-    accM[f] = __dp4a(bytes_ge(d1, kM), 0x01010101u, accM[f]);
+#pragma unroll
+    for (int i = 0; i < STRIP / 4; ++i)
+      accM[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.word(i), pv.word(i)), kM), 0x01010101u, accM[f]);
     h0 = h1; h1 = h2; h2 = h3; h3 = h4; raw_c = raw_n; raw_n = raw_nn;
   }
   // acc = cl + 65536*(ch - cl) (mod 2^32) for lane counts cl, ch  =>  cl + ch = hi16 + 2*lo16
   auto decode_pair = [](uint32_t a) { return ((a >> 16) + 2u * (a & 0xFFFFu)) & 0xFFFFu; };
-  oS = decode_pair(accS[0]) | (decode_pair(accS[1]) << 16);       // top | bottom<<16
-  oL = decode_pair(accL[0]) | (decode_pair(accL[1]) << 16);
-  oM = (accM[0] >> 7) | ((accM[1] >> 7) << 16);                   // dp4a summed 0x80 per hit
+  const int flip = y_first & 1;   // slot 0 holds rows of parity (y_first & 1)
+  const uint32_t s0 = decode_pair(accS[0]), s1 = decode_pair(accS[1]);
+  const uint32_t l0 = decode_pair(accL[0]), l1 = decode_pair(accL[1]);
+  const uint32_t m0 = accM[0] >> 7, m1 = accM[1] >> 7;             // dp4a summed 0x80 per hit
+  oS = flip ? (s1 | (s0 << 16)) : (s0 | (s1 << 16));               // top | bottom<<16
+  oL = flip ? (l1 | (l0 << 16)) : (l0 | (l1 << 16));
+  oM = flip ? (m1 | (m0 << 16)) : (m0 | (m1 << 16));
 }
 
-__global__ void __launch_bounds__(kCombThreads, 3) comb_u8_kernel(const __grid_constant__ CombArgs a) {
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_constant__ CombArgs a) {
+  constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte aligned ring base; pointer arithmetic stays on the __shared__ array so loads compile to LDS
   uint8_t* tiles = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  __shared__ __align__(8) uint64_t full_bar[kCombStages];
+  __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ unsigned int red[2][3];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int strip = tid & 15, run = tid >> 4;
+  constexpr int TPR = kCombTW / Cfg::STRIP;       // threads per row
+  const int strip = tid % TPR, run = tid / TPR;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kCombStages; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 6) (&red[0][0])[tid] = 0u;
@@ -188,36 +220,37 @@ __global__ void __launch_bounds__(kCombThreads, 3) comb_u8_kernel(const __grid_c
     const CUtensorMap* map = &a.map[pl];
     const int lt = seg.tile - P.tile0;
     const int ty = lt / P.tilesX, tx = lt - ty * P.tilesX;
-    const int x0 = tx * kCombTW, y0 = ty * kCombTH;
+    const int x0 = tx * kCombTW, y0 = ty * Cfg::TH;
     const int nf = seg.fend - seg.fbegin;
     const int nloads = nf + 1;                       // L_0 = previous frame, L_k = frame fbegin+k-1
     const int fprev = seg.fbegin > 0 ? seg.fbegin - 1 : seg.fbegin;
-    const bool edge = (y0 < 2) || (y0 + kCombTH + 2 > P.H);
-    const bool rows_live = (y0 + run * kCombR) < P.H;      // thread's run intersects the plane
+    const bool edge = (y0 < 2) || (y0 + Cfg::TH + 2 > P.H);
+    const int y_first = y0 + run * Cfg::R;
+    const bool rows_live = y_first < P.H;            // thread's run intersects the plane
 
     auto issue = [&](int j) {                        // thread 0 only
       const uint32_t g = gload + (uint32_t)j;
-      const int st = g % kCombStages;
+      const int st = g % S;
       const int fr = (j == 0) ? fprev : seg.fbegin + j - 1;
-      mbar_expect_tx(&full_bar[st], kCombStageBytes);
-      tma_load_3d(tiles + st * kCombStageBytes, map, &full_bar[st], x0, y0 - 2, fr);
+      mbar_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+      tma_load_3d(tiles + st * Cfg::STAGE_BYTES, map, &full_bar[st], x0, y0 - 2, fr);
     };
     if (tid == 0) {
-      const int pro = nloads < kCombStages ? nloads : kCombStages;
+      const int pro = nloads < S ? nloads : S;
       for (int j = 0; j < pro; ++j) issue(j);
     }
-    mbar_wait(&full_bar[gload % kCombStages], (gload / kCombStages) & 1u);      // L_0
+    mbar_wait(&full_bar[gload % S], (gload / S) & 1u);      // L_0
     for (int k = 1; k <= nf; ++k) {
       const uint32_t g = gload + (uint32_t)k;
-      const int st = g % kCombStages, stp = (g - 1) % kCombStages;
-      mbar_wait(&full_bar[st], (g / kCombStages) & 1u);
-      const uint8_t* cur = tiles + st * kCombStageBytes + (run * kCombR) * kCombTW + strip * 8;
-      const uint8_t* prv = tiles + stp * kCombStageBytes + (run * kCombR) * kCombTW + strip * 8;
+      const int st = g % S, stp = (g - 1) % S;
+      mbar_wait(&full_bar[st], (g / S) & 1u);
+      const uint8_t* cur = tiles + st * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
+      const uint8_t* prv = tiles + stp * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
       uint32_t vS = 0, vL = 0, vM = 0;
       if (!edge) {
-        comb_tile_rows<false>(cur, prv, y0 + run * kCombR, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
+        comb_tile_rows<Cfg, false>(cur, prv, y_first, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
       } else if (rows_live) {
-        comb_tile_rows<true>(cur, prv, y0 + run * kCombR, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
+        comb_tile_rows<Cfg, true>(cur, prv, y_first, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
       }
       vS = __reduce_add_sync(0xFFFFFFFFu, vS);
       vL = __reduce_add_sync(0xFFFFFFFFu, vL);
@@ -231,7 +264,7 @@ __global__ void __launch_bounds__(kCombThreads, 3) comb_u8_kernel(const __grid_c
         if (v & 0xFFFFu) atomicAdd(o, (int)(v & 0xFFFFu));         // top field   [metric]
         if (v >> 16) atomicAdd(o + 3, (int)(v >> 16));             // bottom field [metric]
       }
-      if (tid == 0 && (k - 1 + kCombStages) < nloads) issue(k - 1 + kCombStages);
+      if (tid == 0 && (k - 1 + S) < nloads) issue(k - 1 + S);
       ++gstep;
     }
     gload += (uint32_t)nloads;

@@ -44,6 +44,11 @@ AMTK_API int amtk_ctx_synchronize(amtk_ctx* ctx);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 AMTK_API int64_t amtk_ctx_launch_count(const amtk_ctx* ctx);
 
+/* Per-launch timing of the dominant streaming kernel (comb) with CUDA events recorded on the context's stream
+ * around each launch; get() synchronizes the stream, returns the accumulated milliseconds and launch count. */
+AMTK_API int amtk_ctx_set_kernel_timing(amtk_ctx* ctx, int enable);
+AMTK_API int amtk_ctx_get_kernel_timing(amtk_ctx* ctx, double* ms_total, int64_t* launches, int reset);
+
 /* Pinned host memory for the host-buffer entry points (optional; pageable memory works, only slower). */
 AMTK_API int amtk_host_alloc(size_t bytes, void** out);
 AMTK_API void amtk_host_free(void* p);

@@ -386,8 +386,30 @@ def ref_lib():
         R.ref_scan_normalize.argtypes = [V, C.c_int]
         R.ref_scan_get_logo.restype = C.c_int
         R.ref_scan_get_logo.argtypes = [V, C.c_int, c_float_p]
+        R.ref_bench_scan_comb_u8.restype = C.c_double
+        R.ref_bench_scan_comb_u8.argtypes = [V, c_u8_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int, c_float_p, c_i32_p]
         _ref = R
     return _ref
+
+
+def cpu_scan_comb(frames, w, h, logo_data, imgx, imgy, th6, nthreads, maskratio=0.35, logo_w=64, logo_h=64):
+    """Bounded CPU run of the fused hot path (ScanFrame + comb) over packed-YV12 `frames` (numpy uint8 (n, w*h*3/2)).
+    Uses the reference's own compiled code for the logo half when oracle/_ref exists ("reference"), else the
+    plain-C port ("port").  Returns (seconds, scores (n,2), counts (n,12), kind)."""
+    fr = np.ascontiguousarray(frames, np.uint8)
+    n = fr.shape[0]
+    scores = np.zeros((n, 2), np.float32)
+    counts = np.zeros((n, 12), np.int32)
+    th = np.asarray(th6, np.int32)
+    if ref_available():
+        lg = RefLogo.create(logo_data, logo_w, logo_h, w, h, imgx, imgy).deint().create_mask(maskratio)
+        sec = ref_lib().ref_bench_scan_comb_u8(lg.ptr, _p(fr, c_u8_p), n, w, h, _p(th, c_i32_p), nthreads,
+                                               _p(scores, c_float_p), _p(counts, c_i32_p))
+        return sec, scores, counts, "reference"
+    lg = OracleLogo.create(logo_data, logo_w, logo_h, w, h, imgx, imgy).deint().create_mask(maskratio)
+    sec = oracle_lib().amtk_or_bench_scan_comb_u8(lg.ptr, _p(fr, c_u8_p), n, w, h, _p(th, c_i32_p), nthreads,
+                                                  _p(scores, c_float_p), _p(counts, c_i32_p))
+    return sec, scores, counts, "port"
 
 
 class RefLogo:

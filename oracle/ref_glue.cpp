@@ -143,4 +143,42 @@ int ref_scan_get_logo(void* p, int clean, float* out) {
   return 1;
 }
 
+/* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline leg) ----------------------------
+ * Per frame: LogoFrame::ScanFrame (LogoScan.hpp:1559-1566) with the reference's OWN DeintY + EvaluateLogo
+ * (incl. CalcCorrelation5x5_AVX), followed by the combing metric, which the reference does not contain and is
+ * therefore this repo's scalar spec (amtk_or_comb_frame_u8, linked in from oracle/amtk_oracle.c).
+ * frames: packed YV12.  OpenMP over independent frames; each thread owns a private LogoDataParam clone because
+ * EvaluateLogo is only re-entrant across distinct scratch buffers.  Returns wall seconds. */
+void amtk_or_comb_frame_u8(const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                           int, int, int, int, int, int, const int*, int32_t*);
+}
+#include <time.h>
+#include <omp.h>
+extern "C" {
+double ref_bench_scan_comb_u8(void* deint_logo, const uint8_t* frames, int nframes, int w, int h, const int* th6,
+                              int nthreads, float* out_scores, int32_t* out_counts) {
+  LogoDataParam* lg = (LogoDataParam*)deint_logo;
+  const size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2), fsz = ysz + 2 * csz;
+  const int n = lg->w * lg->h;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<float> deint((size_t)n + 8), work((size_t)n + 8);
+#pragma omp for schedule(static)
+    for (int i = 0; i < nframes; ++i) {
+      const uint8_t* cur = frames + (size_t)i * fsz;
+      const uint8_t* prev = frames + (size_t)(i > 0 ? i - 1 : 0) * fsz;
+      int off = lg->imgx + lg->imgy * w;
+      DeintY<uint8_t>(deint.data(), cur + off, w, lg->w, lg->h);
+      out_scores[(size_t)i * 2 + 0] = lg->EvaluateLogo(deint.data(), 255.0f, 0, work.data());
+      out_scores[(size_t)i * 2 + 1] = lg->EvaluateLogo(deint.data(), 255.0f, 1, work.data());
+      amtk_or_comb_frame_u8(cur, cur + ysz, cur + ysz + csz, prev, prev + ysz, prev + ysz + csz,
+                            w, h, w, w / 2, 1, 1, th6, out_counts + (size_t)i * 12);
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
 } /* extern "C" */
