@@ -185,23 +185,25 @@ static int comb_thresholds_ok(const amtk_comb_params* p) {
 
 // Everything the host needs to know about one compiled comb-kernel variant.
 struct CombVariant {
-  int R, strip, stages, TH, boxH, threads, smem;
+  int R, strip, stages, acc, TH, boxH, threads, smem;
   void (*kernel)(const CombArgs);
 };
 template <typename Cfg> static CombVariant make_variant() {
-  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_u8_kernel<Cfg> };
+  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::ACC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_u8_kernel<Cfg> };
 }
 static const CombVariant* comb_variants(int* n) {
   static const CombVariant v[] = {
-    make_variant<CombCfg<15, 8, 4>>(), make_variant<CombCfg<16, 8, 4>>(), make_variant<CombCfg<17, 8, 4>>(),
-    make_variant<CombCfg<15, 8, 3>>(), make_variant<CombCfg<16, 8, 3>>(), make_variant<CombCfg<17, 8, 3>>(),
-    make_variant<CombCfg<15, 4, 4>>(), make_variant<CombCfg<16, 4, 4>>(), make_variant<CombCfg<17, 4, 4>>(),
-    make_variant<CombCfg<15, 4, 3>>(), make_variant<CombCfg<16, 4, 3>>(), make_variant<CombCfg<17, 4, 3>>(),
+    make_variant<CombCfg<15, 8, 3, 0>>(), make_variant<CombCfg<16, 8, 3, 0>>(), make_variant<CombCfg<17, 8, 3, 0>>(),
+    make_variant<CombCfg<15, 8, 3, 1>>(), make_variant<CombCfg<16, 8, 3, 1>>(), make_variant<CombCfg<17, 8, 3, 1>>(),
+    make_variant<CombCfg<15, 8, 3, 2>>(), make_variant<CombCfg<16, 8, 3, 2>>(), make_variant<CombCfg<17, 8, 3, 2>>(),
+    make_variant<CombCfg<17, 8, 4, 0>>(), make_variant<CombCfg<17, 8, 4, 1>>(), make_variant<CombCfg<17, 8, 4, 2>>(),
+    make_variant<CombCfg<15, 8, 2, 0>>(), make_variant<CombCfg<16, 8, 2, 0>>(), make_variant<CombCfg<17, 8, 2, 0>>(),
+    make_variant<CombCfg<17, 4, 2, 0>>(), make_variant<CombCfg<17, 4, 3, 0>>(),
   };
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }
-static int g_comb_strip = 8, g_comb_stages = 4, g_comb_R = 0, g_comb_ctas_per_sm = 0;   // tuning knobs (env AMTK_COMB_*)
+static int g_comb_strip = 8, g_comb_stages = 3, g_comb_R = 0, g_comb_ctas_per_sm = 0, g_comb_acc = 0, g_comb_l2 = 128;   // tuning knobs (env AMTK_COMB_*)
 
 // rows per run: the R in {15,16,17} that wastes the fewest rows over luma + chroma (1080/540 -> 17, 720/360 -> 15)
 static int pick_comb_R(int hY, int hC) {
@@ -224,7 +226,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   const int hY = clip->height, hC = clip->height >> clip->log_uvy;
   const int R = g_comb_R ? g_comb_R : pick_comb_R(hY, hC);
   int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
-  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == g_comb_strip && vars[i].stages == g_comb_stages) V = &vars[i];
+  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == g_comb_strip && vars[i].stages == g_comb_stages && vars[i].acc == g_comb_acc) V = &vars[i];
   if (!V) AMTK_FAIL("comb: no kernel variant for the requested AMTK_COMB_* settings");
   CombArgs args;
   memset(&args, 0, sizeof(args));
@@ -250,7 +252,9 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     CUresult r = ctx->encode_tiled(&args.map[pl], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                                    const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                   g_comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : g_comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                   g_comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) AMTK_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   }
   const int ntiles = tile0;
@@ -355,6 +359,8 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_STAGES")) g_comb_stages = atoi(e);
   if (const char* e = getenv("AMTK_COMB_R")) g_comb_R = atoi(e);
   if (const char* e = getenv("AMTK_COMB_CTAS")) g_comb_ctas_per_sm = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_ACC")) g_comb_acc = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_L2")) g_comb_l2 = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }
   *out = c;

@@ -32,9 +32,11 @@ constexpr int kCombRuns = 8;            // vertical runs per tile (one per half-
 
 // Compile-time shape of one kernel variant: R rows per run (tile height 8R), STRIP pixels per thread-row,
 // STAGES ring slots.
-template <int R_, int STRIP_, int STAGES_>
+// ACC selects how threshold hits are counted: 0 = integer masks + IADD3 (ALU pipe), 1 = lshima as fp16 1.0s +
+// HADD2 (FMA pipe), 2 = both numeric (pipe balancing knob; results are identical).
+template <int R_, int STRIP_, int STAGES_, int ACC_ = 0>
 struct CombCfg {
-  static constexpr int R = R_, STRIP = STRIP_, STAGES = STAGES_;
+  static constexpr int R = R_, STRIP = STRIP_, STAGES = STAGES_, ACC = ACC_;
   static constexpr int TH = kCombRuns * R;                 // output rows per tile
   static constexpr int BOXH = TH + 4;                      // with +-2 halo rows
   static constexpr int STAGE_BYTES = kCombTW * BOXH;
@@ -139,6 +141,8 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
   const __half2 thL = *reinterpret_cast<const __half2*>(&thL_bits);
   const __half2 k4 = __float2half2_rn(4.0f), km3 = __float2half2_rn(-3.0f);
   uint32_t accS[2] = { 0u, 0u }, accL[2] = { 0u, 0u }, accM[2] = { 0u, 0u };
+  __half2 fS[2], fL[2];
+  fS[0] = fS[1] = fL[0] = fL[1] = __float2half2_rn(0.0f);
 
   RawRow<STRIP> raw_c, raw_n, rtmp;
   rtmp.load(cur);                 HRow<NQ> h0 = bytes_to_half<STRIP>(rtmp);
@@ -151,6 +155,7 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
     const HRow<NQ> h4 = bytes_to_half<STRIP>(raw_nn);
     RawRow<STRIP> pv; pv.load(prev + (j + 2) * kCombTW);
     const int f = j & 1;          // accumulator slot; mapped to the field parity after the loop
+    // rows y < 2 and y >= H-2 have no comb response (spec): an infinite threshold switches them off
     __half2 tS = thS, tL = thL;
     if (EDGE) {
       const int y = y_first + j;
@@ -159,18 +164,22 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
 #pragma unroll
     for (int q = 0; q < NQ; q += 2) {
       uint32_t mS[2], mL[2];
+      __half2 nS[2], nL[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         __half2 t = __hadd2(h0.v[q + e], h4.v[q + e]);
         t = __hfma2(k4, h2.v[q + e], t);
         const __half2 u = __hadd2(h1.v[q + e], h3.v[q + e]);
         const __half2 r = __habs2(__hfma2(km3, u, t));
-        mS[e] = __hge2_mask(r, tS);
-        mL[e] = __hge2_mask(r, tL);
+        if (Cfg::ACC >= 2) nS[e] = __hge2(r, tS); else mS[e] = __hge2_mask(r, tS);
+        if (Cfg::ACC >= 1) nL[e] = __hge2(r, tL); else mL[e] = __hge2_mask(r, tL);
       }
-      // 0xFFFF-per-lane masks are subtracted as plain 32-bit integers; decode_pair() undoes the lane coupling
-      accS[f] = accS[f] - mS[0] - mS[1];
-      accL[f] = accL[f] - mL[0] - mL[1];
+      // integer mode: 0xFFFF-per-lane masks are subtracted as plain 32-bit integers; decode_pair() undoes the
+      // lane coupling.  numeric mode: 1.0s are summed in fp16 (exact: <= 2*R per lane).
+      if (Cfg::ACC >= 2) { fS[f] = __hadd2(fS[f], nS[0]); fS[f] = __hadd2(fS[f], nS[1]); }
+      else accS[f] = accS[f] - mS[0] - mS[1];
+      if (Cfg::ACC >= 1) { fL[f] = __hadd2(fL[f], nL[0]); fL[f] = __hadd2(fL[f], nL[1]); }
+      else accL[f] = accL[f] - mL[0] - mL[1];
     }
     // inter-frame difference of the centre row, 4 pixels per op
 #pragma unroll
@@ -181,8 +190,11 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
   // acc = cl + 65536*(ch - cl) (mod 2^32) for lane counts cl, ch  =>  cl + ch = hi16 + 2*lo16
   auto decode_pair = [](uint32_t a) { return ((a >> 16) + 2u * (a & 0xFFFFu)) & 0xFFFFu; };
   const int flip = y_first & 1;   // slot 0 holds rows of parity (y_first & 1)
-  const uint32_t s0 = decode_pair(accS[0]), s1 = decode_pair(accS[1]);
-  const uint32_t l0 = decode_pair(accL[0]), l1 = decode_pair(accL[1]);
+  auto decode_half = [](__half2 h) { return (uint32_t)(__half2float(__low2half(h)) + __half2float(__high2half(h))); };
+  const uint32_t s0 = Cfg::ACC >= 2 ? decode_half(fS[0]) : decode_pair(accS[0]);
+  const uint32_t s1 = Cfg::ACC >= 2 ? decode_half(fS[1]) : decode_pair(accS[1]);
+  const uint32_t l0 = Cfg::ACC >= 1 ? decode_half(fL[0]) : decode_pair(accL[0]);
+  const uint32_t l1 = Cfg::ACC >= 1 ? decode_half(fL[1]) : decode_pair(accL[1]);
   const uint32_t m0 = accM[0] >> 7, m1 = accM[1] >> 7;             // dp4a summed 0x80 per hit
   oS = flip ? (s1 | (s0 << 16)) : (s0 | (s1 << 16));               // top | bottom<<16
   oL = flip ? (l1 | (l0 << 16)) : (l0 | (l1 << 16));
