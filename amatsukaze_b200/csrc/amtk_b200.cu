@@ -69,7 +69,8 @@ static int for_each_window(amtk_ctx* ctx, const amtk_clip* clip, int frame0, int
     return fn(w, frame0, frame0 + nframes);
   }
   const size_t fs = (size_t)clip->frame_stride;
-  const size_t budget = (size_t)256 << 20;
+  size_t budget = (size_t)256 << 20;          // HBM staging per buffer (two buffers); AMTK_STAGE_MB overrides (tests)
+  if (const char* e = getenv("AMTK_STAGE_MB")) budget = (size_t)std::max(1, atoi(e)) << 20;
   int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)nframes, budget / fs));
   if (need_prev && per > 1) per -= 1;
   const size_t need = (size_t)(per + (need_prev ? 1 : 0)) * fs;
@@ -121,7 +122,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     AMTK_FAIL("logo has no feature pixels");
   }
   const int countPad = sp.logo->countPad;
-  const size_t smem = ((size_t)((sp.roi_w * sp.roi_h + 3) & ~3) + (size_t)hl.w * hl.h + 8) * sizeof(float);
+  const size_t smem = logo_scores_smem_bytes(sp.roi_w * sp.roi_h, hl.w * hl.h, clip->bytes_per_sample);
   if (smem > 200 * 1024) AMTK_FAIL("logo too large for the shared-memory evaluation path");
   // frames per launch bounded by the score scratch (<= 96 MB)
   const size_t per_frame = (size_t)sp.nfades * countPad * sizeof(float);
@@ -155,7 +156,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
 #undef AMTK_LAUNCH_SCORES
     AMTK_CUDA(cudaGetLastError());
     const int total = n * sp.nfades;
-    logo_sum_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(
+    logo_sum_kernel<<<(total + kSumThreads - 1) / kSumThreads, kSumThreads, 0, ctx->stream>>>(
         job.scores, count, countPad, n, sp.nfades, hl.blackScore, sp.take_abs,
         dout + (size_t)(f0 - out_row0) * out_frame_stride, out_frame_stride, sp.out_off, sp.out_fade_stride);
     AMTK_CUDA(cudaGetLastError());

@@ -39,16 +39,33 @@ struct EvalJob {
   float* scores;             // [nframes][nfades][countPad]
 };
 
+// Shared-memory layout of logo_scores_kernel (floats unless noted):
+//   A[npx] B[npx]      logo planes, loaded once per CTA
+//   src[roi_n]         the frame's ROI as float (DeintY or CopyY)
+//   work[npx + 8]      logo-removed image of the current fade
+//   raw[roi_n]         pixel_t: the ROI bytes of the NEXT frame of this CTA (register-prefetched, then staged)
+__host__ __device__ inline size_t logo_scores_smem_bytes(int roi_n, int npx, int bytes_per_sample) {
+  return ((size_t)2 * ((npx + 3) & ~3) + ((roi_n + 3) & ~3) + (size_t)npx + 8) * sizeof(float) +
+         (((size_t)roi_n * bytes_per_sample + 15) & ~(size_t)15);
+}
+
+constexpr int kRoiPrefetch = 8;    // ROI elements per thread held in registers for the next frame (ROIs up to 4096 px)
+
 template <typename pixel_t, int PXT>
 __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const EvalJob job) {
   extern __shared__ float smem_f[];
-  float* src = smem_f;                                           // roi_w*roi_h
-  float* work = smem_f + ((job.roi_w * job.roi_h + 3) & ~3);     // logo.w*logo.h (+8 pad)
   const int tid = threadIdx.x;
   const LogoDev& lg = job.logo;
   const int w = lg.w, npx = lg.w * lg.h;
+  const int roi_n = job.roi_w * job.roi_h;
+  float* sA = smem_f;
+  float* sB = sA + ((npx + 3) & ~3);
+  float* src = sB + ((npx + 3) & ~3);
+  float* work = src + ((roi_n + 3) & ~3);
+  pixel_t* raw = reinterpret_cast<pixel_t*>(work + npx + 8);
 
-  // ---- one-time: adopt feature pixels, pull their taps into registers ----
+  // ---- one-time: logo planes to smem, adopt feature pixels, pull their taps into registers ----
+  for (int i = tid; i < npx; i += kEvalThreads) { sA[i] = lg.A[i]; sB[i] = lg.B[i]; }
   float taps[PXT][25];
   int pxy[PXT];
   int cidx[PXT];
@@ -67,24 +84,60 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const Eval
       for (int t = 0; t < 25; ++t) taps[p][t] = 0.0f;
     }
   }
+  // per-thread walk over image indices i = tid, tid+512, ... without divisions: (x,y) advance by (dx,dy)
+  const int roi_dx = kEvalThreads % job.roi_w, roi_dy = kEvalThreads / job.roi_w;
+  const int roi_y0 = tid / job.roi_w, roi_x0 = tid - roi_y0 * job.roi_w;
+  const int lg_dx = kEvalThreads % w, lg_dy = kEvalThreads / w;
+  const int lg_y0 = tid / w, lg_x0 = tid - lg_y0 * w;
+  const bool prefetch_ok = roi_n <= kRoiPrefetch * kEvalThreads;
 
-  const int roi_n = job.roi_w * job.roi_h;
-  for (int f = blockIdx.y; f < job.nframes; f += gridDim.y) {
-    // ---- stage the ROI as float: DeintY (:763-780) or CopyY (:782-790) ----
+  auto roi_ptr = [&](int f) {
     const pixel_t* fr = reinterpret_cast<const pixel_t*>(
         reinterpret_cast<const uint8_t*>(job.ybase) + (long long)(job.frame0 + f) * job.frame_stride);
-    const pixel_t* roi = fr + job.imgx + (long long)job.imgy * job.pitch;
-    for (int i = tid; i < roi_n; i += kEvalThreads) {
-      const int y = i / job.roi_w, x = i - y * job.roi_w;
-      const pixel_t* p = roi + x + (long long)y * job.pitch;
-      float v;
-      if (job.src_mode == 0 && y > 0 && y < job.roi_h - 1) {
-        const int a = p[-job.pitch], b = p[0], c = p[job.pitch];
-        v = (float)(a + 2 * b + c + 2) / 4.0f;       // exact: integer < 2^24, division by 4
-      } else {
-        v = (float)p[0];
+    return fr + job.imgx + (long long)job.imgy * job.pitch;
+  };
+  pixel_t pre[kRoiPrefetch];
+  auto fetch = [&](int f) {         // coalesced element loads of the frame's ROI into registers
+    const pixel_t* roi = roi_ptr(f);
+    int x = roi_x0, y = roi_y0;
+#pragma unroll
+    for (int k = 0; k < kRoiPrefetch; ++k) {
+      if (tid + k * kEvalThreads < roi_n) pre[k] = roi[x + (long long)y * job.pitch];
+      x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
+    }
+  };
+  int f = blockIdx.y;
+  if (prefetch_ok && f < job.nframes) fetch(f);
+  __syncthreads();
+  for (; f < job.nframes; f += gridDim.y) {
+    // ---- stage the ROI bytes (prefetched registers, or direct loads for very large ROIs) ----
+    if (prefetch_ok) {
+#pragma unroll
+      for (int k = 0; k < kRoiPrefetch; ++k) if (tid + k * kEvalThreads < roi_n) raw[tid + k * kEvalThreads] = pre[k];
+    } else {
+      const pixel_t* roi = roi_ptr(f);
+      int x = roi_x0, y = roi_y0;
+      for (int i = tid; i < roi_n; i += kEvalThreads) {
+        raw[i] = roi[x + (long long)y * job.pitch];
+        x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
       }
-      src[i] = v;
+    }
+    __syncthreads();
+    if (prefetch_ok && f + (int)gridDim.y < job.nframes) fetch(f + gridDim.y);   // in flight during this frame's math
+    // ---- ROI as float: DeintY (:763-780) or CopyY (:782-790) ----
+    {
+      int x = roi_x0, y = roi_y0;
+      for (int i = tid; i < roi_n; i += kEvalThreads) {
+        float v;
+        if (job.src_mode == 0 && y > 0 && y < job.roi_h - 1) {
+          const int a = raw[i - job.roi_w], b = raw[i], c = raw[i + job.roi_w];
+          v = (float)(a + 2 * b + c + 2) / 4.0f;       // exact: integer < 2^24, division by 4
+        } else {
+          v = (float)raw[i];
+        }
+        src[i] = v;
+        x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
+      }
     }
     __syncthreads();
 
@@ -92,24 +145,32 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const Eval
       const float fade = job.fades[fi];
       const float omf = AMTK_FSUB(1.0f, fade);
       // ---- logo removal at this fade level (LogoScan.hpp:241-251) ----
-      for (int i = tid; i < npx; i += kEvalThreads) {
-        const int y = i / w, x = i - y * w;
-        const float srcv = src[job.src_off + x + y * job.src_stride];
-        work[i] = remove_logo(srcv, __ldg(lg.A + i), __ldg(lg.B + i), job.maxv, fade, omf);
+      {
+        int x = lg_x0, y = lg_y0;
+        for (int i = tid; i < npx; i += kEvalThreads) {
+          const float srcv = src[job.src_off + x + y * job.src_stride];
+          work[i] = remove_logo(srcv, sA[i], sB[i], job.maxv, fade, omf);
+          x += lg_dx; y += lg_dy; if (x >= w) { x -= w; ++y; }
+        }
       }
       __syncthreads();
       // ---- per-feature score (LogoScan.hpp:298-308) ----
       float* out = job.scores + ((size_t)f * job.nfades + fi) * lg.countPad;
+      float sums[PXT]; int bins[PXT];
 #pragma unroll
       for (int p = 0; p < PXT; ++p) {
-        if (cidx[p] < lg.count) {
-          const float* wp = work + pxy[p];
-          float avg;
-          const float sum = corr5x5_tree(taps[p], [&](int dy, int dx) { return wp[dy * w + dx]; }, &avg);
-          const float2 sc = __ldg(lg.scales + (size_t)cidx[p] * 32 + scale_bin(avg));
-          out[cidx[p]] = pixel_score(sum, sc.x, sc.y);
-        }
+        const float* wp = work + pxy[p];
+        float avg;
+        sums[p] = corr5x5_tree(taps[p], [&](int dy, int dx) { return wp[dy * w + dx]; }, &avg);
+        bins[p] = scale_bin(avg);
       }
+      float2 sc[PXT];
+#pragma unroll
+      for (int p = 0; p < PXT; ++p)      // all scale gathers in flight together
+        sc[p] = (cidx[p] < lg.count) ? __ldg(lg.scales + (size_t)cidx[p] * 32 + bins[p]) : make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int p = 0; p < PXT; ++p)
+        if (cidx[p] < lg.count) out[cidx[p]] = pixel_score(sums[p], sc[p].x, sc[p].y);
       __syncthreads();     // `work` is rewritten by the next fade / `src` by the next frame
     }
   }
@@ -117,24 +178,45 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const Eval
 
 // One thread per (frame, fade): ordered float sum of the pixel scores, divided by blackScore (:252-254,310).
 // out index = frame*out_frame_stride + out_off + fade*out_fade_stride; take_abs for AMTAnalyzeLogo (:1152-1154).
-__global__ void __launch_bounds__(128) logo_sum_kernel(const float* __restrict__ scores, int count, int countPad,
-                                                       int nframes, int nfades, float blackScore, int take_abs,
-                                                       float* __restrict__ out, int out_frame_stride, int out_off,
-                                                       int out_fade_stride) {
+// The chain of ~1.3k dependent FADDs is inherent (the order is the reference's); the loads are software-pipelined
+// one 128-byte line ahead so the chain never waits on memory.  32-thread blocks spread the chains over all SMs.
+constexpr int kSumThreads = 32;
+__global__ void __launch_bounds__(kSumThreads) logo_sum_kernel(const float* __restrict__ scores, int count, int countPad,
+                                                               int nframes, int nfades, float blackScore, int take_abs,
+                                                               float* __restrict__ out, int out_frame_stride, int out_off,
+                                                               int out_fade_stride) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nframes * nfades) return;
-  const float4* row = reinterpret_cast<const float4*>(scores + (size_t)t * countPad);
+  const float4* row = reinterpret_cast<const float4*>(scores + (size_t)t * countPad);   // countPad % 32 == 0
+  const int nlines = countPad >> 5;            // 32 floats (8 float4) per line; padding reads stay inside the row
+  float4 cur[8], nxt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cur[k] = row[k];
   float r = 0.0f;
-  const int n4 = count >> 2;
   int c = 0;
-#pragma unroll 4
-  for (int i = 0; i < n4; ++i) {
-    const float4 v = row[i];
-    r = AMTK_FADD(r, v.x); r = AMTK_FADD(r, v.y); r = AMTK_FADD(r, v.z); r = AMTK_FADD(r, v.w);
+  for (int l = 0; l < nlines; ++l) {
+    if (l + 1 < nlines) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nxt[k] = row[(l + 1) * 8 + k];
+    }
+    if (c + 32 <= count) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        r = AMTK_FADD(r, cur[k].x); r = AMTK_FADD(r, cur[k].y); r = AMTK_FADD(r, cur[k].z); r = AMTK_FADD(r, cur[k].w);
+      }
+      c += 32;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (c < count) r = AMTK_FADD(r, cur[k].x); ++c;
+        if (c < count) r = AMTK_FADD(r, cur[k].y); ++c;
+        if (c < count) r = AMTK_FADD(r, cur[k].z); ++c;
+        if (c < count) r = AMTK_FADD(r, cur[k].w); ++c;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
   }
-  c = n4 << 2;
-  const float* tail = scores + (size_t)t * countPad;
-  for (; c < count; ++c) r = AMTK_FADD(r, tail[c]);
   float v = AMTK_FDIV(r, blackScore);
   if (take_abs) v = fabsf(v);
   const int f = t / nfades, fi = t - f * nfades;

@@ -88,7 +88,7 @@ def _plane(n, H, W, plane, seed, mode, speed):
         bad = (_hash32(n, n * 0 + 11, n * 0, 5, seed) % 10) < 3          # ~30 % of frames get a gradient -> fail thy
         v = g + ((_hash32(x, y, n, plane, seed) & 3) - 2)
         if plane == 0:
-            v = v + torch.where(bad, (x * 40) // W, torch.zeros_like(x))
+            v = v + torch.where(bad, x & 63, torch.zeros_like(x))      # sawtooth: any ROI >= 32 px wide fails thy
         return v
     par = y & 1
     t = _field_time(n, par, mode)                                        # (N,H,1)

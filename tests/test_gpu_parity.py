@@ -97,3 +97,182 @@ def test_fused_and_host_path(ctx, oracle):
     host = fr.cpu().numpy()
     s2, c2 = ctx.scan_comb_frames(_clip(host, W, H, on_device=False), [P["deint"]], prm)
     assert np.array_equal(_bits(s2[:, 0]), _bits(rs)) and np.array_equal(c2, rc)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# golden fixtures (produced by the reference's own code, tests/golden/gen_golden.py) through the C ABI
+# ----------------------------------------------------------------------------------------------------------------
+import json
+import os
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "logo_golden.json")))
+
+
+def test_golden_scan_and_analyze(ctx):
+    lg = synth.make_logo(64, 64, seed=1)
+    fr = synth.make_frames(40, 24, W, H, seed=0x5EED0001, device="cuda", logo=lg, imgx=IMGX, imgy=IMGY, logo_period=20)
+    raw = ab.Logo.create(lg["data"], 64, 64, W, H, IMGX, IMGY)
+    de, top, bot = raw.deint().create_mask(0.35), raw.field(0).create_mask(0.35), raw.field(1).create_mask(0.35)
+    clip = _clip(fr, W, H)
+    out = ctx.scan_frames(clip, [de]).cpu().numpy()
+    assert [_bits(out[i, 0]).tolist() for i in range(24)] == GOLD["scan_frame_bits"]
+    an = ctx.analyze_frames(clip, de, top, bot).cpu().numpy()
+    for k, i in enumerate(GOLD["analyze_frames"]):
+        assert _bits(an[i]).tolist() == GOLD["analyze_bits"][k]
+    de10 = raw.deint().create_mask(0.1)
+    fades = (np.float32(0.1) * np.arange(20, dtype=np.float32)).astype(np.float32)       # LogoScan.hpp:967
+    sweep = ctx.eval_fades(clip, de10, fades, frame0=12, nframes=1).cpu().numpy()
+    assert _bits(sweep[0]).tolist() == GOLD["fade_sweep_bits"]
+
+
+def test_scan_frames_16bit(ctx, oracle):
+    """YUV420P10: maxv=1023, u16 samples; also the reference's byte-pitch quirk (LogoScan.hpp:1547,1561)."""
+    po = oracle
+    w, h, imgx, imgy = 256, 128, 96, 16
+    lg, P, O = _logos(po, imgw=w, imgh=h, imgx=imgx, imgy=imgy)
+    n = 6
+    f8 = synth.make_frames(50, n, w, h, device="cuda", logo=lg, imgx=imgx, imgy=imgy, logo_period=20)
+    f16 = (f8.to(torch.int32) * 4 + 1).to(torch.int16).contiguous()       # 10-bit range, packed like the 8-bit clip
+    clip = ab.yv12_clip(f16, w, h, n, True, bits=10)
+    out = ctx.scan_frames(clip, [P["deint"]]).cpu().numpy()
+    Y16 = f16.cpu().numpy().view(np.uint16)[:, : w * h].reshape(n, h, w)
+    ref = np.stack([O["deint"].scan_frame(Y16[i], maxv=1023.0) for i in range(n)])
+    assert np.array_equal(_bits(out[:, 0]), _bits(ref))
+    # quirk: element pitch = byte pitch (rows 2x apart); only legal while the doubled rows stay inside the plane
+    with pytest.raises(ab.AmtkError, match="outside the frame"):
+        ctx.scan_frames(clip, [P["deint"]], pitch_elems_override=2 * w)          # rows 2*(16..79) leave the plane
+    lg0, P0, O0 = _logos(po, imgw=w, imgh=h, imgx=imgx, imgy=0)
+    out_q = ctx.scan_frames(clip, [P0["deint"]], pitch_elems_override=2 * w).cpu().numpy()
+    ref_q = np.stack([O0["deint"].scan_frame(Y16[i].reshape(h // 2, 2 * w), pitch=2 * w, maxv=1023.0) for i in range(n)])
+    assert np.array_equal(_bits(out_q[:, 0]), _bits(ref_q))
+
+
+def test_comb_thresholds_and_ragged_shapes(ctx, oracle):
+    po = oracle
+    prm = ab.default_comb_params()
+    prm.th_move_y, prm.th_shima_y, prm.th_lshima_y = 1, 1, 2047
+    prm.th_move_c, prm.th_shima_c, prm.th_lshima_c = 128, 700, 701
+    for (w, h, n) in ((160, 34, 3), (128, 272, 5), (1952, 36, 2), (32, 1100, 2)):
+        fr = synth.make_frames(3, n, w, h, device="cuda", mode="interlaced")
+        out = ctx.comb_frames(_clip(fr, w, h), prm).cpu().numpy()
+        Y, U, V = synth.split_planes(fr, w, h)
+        assert np.array_equal(out, po.or_comb_clip(Y, U, V, prm.as_list())), (w, h)
+    # extreme content: max-contrast alternating rows -> every pixel combs at the maximum response 1530
+    w, h = 256, 128
+    fr = torch.zeros((2, w * h * 3 // 2), dtype=torch.uint8, device="cuda")
+    Yv = fr[:, : w * h].view(2, h, w)
+    Yv[:, 0::2, :] = 255
+    prm2 = ab.default_comb_params()
+    prm2.th_shima_y, prm2.th_lshima_y = 1530, 1531
+    out = ctx.comb_frames(_clip(fr, w, h), prm2).cpu().numpy()
+    assert out[0, 1] + out[0, 4] == (h - 4) * w and out[0, 2] + out[0, 5] == 0 and out[:, 0].sum() == 0
+    with pytest.raises(ab.AmtkError, match="th_move"):
+        bad = ab.default_comb_params()
+        bad.th_move_y = 0
+        ctx.comb_frames(_clip(fr, w, h), bad)
+
+
+def test_comb_range_sharding_and_chunked_host_path(ctx, oracle, monkeypatch):
+    """Frame-range calls with a halo frame reproduce the whole-clip result (multi-GPU range sharding), and the
+    host path stays exact when staging is forced into many small chunks."""
+    po = oracle
+    w, h, n = 352, 288, 23
+    fr = synth.make_frames(0, n, w, h, device="cuda", mode="telecine")
+    clip = _clip(fr, w, h)
+    prm = ab.default_comb_params()
+    whole = ctx.comb_frames(clip, prm).cpu().numpy()
+    parts = np.concatenate([ctx.comb_frames(clip, prm, frame0=a, nframes=b - a).cpu().numpy() for a, b in ((0, 7), (7, 8), (8, 23))])
+    assert np.array_equal(whole, parts)
+    Y, U, V = synth.split_planes(fr, w, h)
+    assert np.array_equal(whole, po.or_comb_clip(Y, U, V, prm.as_list()))
+    # telecine: 2 of every 5 frames are combed -> their shima counts dominate
+    sh = whole[:, 1] + whole[:, 4]
+    assert sh[[2, 3]].min() > sh[[0, 1, 4]].max()
+    monkeypatch.setenv("AMTK_STAGE_MB", "1")          # 1 MiB staging -> ~6 frames per chunk
+    host = fr.cpu().numpy()
+    lg, P, O = _logos(po, imgw=w, imgh=h, imgx=200, imgy=100)
+    s, c = ctx.scan_comb_frames(_clip(host, w, h, on_device=False), [P["deint"]], prm)
+    assert np.array_equal(c, whole)
+    rs = np.stack([O["deint"].scan_frame(Y[i]) for i in range(n)])
+    assert np.array_equal(_bits(s[:, 0]), _bits(rs))
+
+
+def test_logoscan_accumulate_matches_oracle(ctx, oracle):
+    po = oracle
+    w, h, sx, sy, sw, sh = 320, 192, 200, 64, 64, 48
+    n = 60
+    lg = synth.make_logo(sw, sh, seed=4)
+    fr = synth.make_frames(0, n, w, h, seed=0x5EED0004, device="cuda", mode="flat", logo=lg, imgx=sx, imgy=sy)
+    clip = _clip(fr, w, h)
+    acc = ctx.logo_scan(sw, sh, 12)
+    valid = acc.add_frames(clip, sx, sy, 0, 40)
+    valid2 = acc.add_frames(clip, sx, sy, 40, 20)            # accumulates across calls
+    Y, U, V = synth.split_planes(fr, w, h)
+    o = po.OracleScan(sw, sh, 12)
+    ov = [o.add_frame(Y[i][sy:sy + sh, sx:sx + sw], U[i][sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2],
+                      V[i][sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2]) for i in range(n)]
+    assert np.concatenate([valid, valid2]).tolist() == ov and 0 < sum(ov) < n
+    assert acc.num_valid == o.nframes
+    assert np.array_equal(acc.sums(), o.sums())              # exact integers in doubles
+    for clean in (False, True):
+        a, b = acc.get_logo(255, clean), o.get_logo(255, clean)
+        assert a is not None and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # frame_select (ReMakeLogo's minFades filter): only selected frames are offered
+    acc2 = ctx.logo_scan(sw, sh, 12)
+    sel = (np.arange(n) % 3 == 0).astype(np.uint8)
+    v2 = acc2.add_frames(clip, sx, sy, select=sel)
+    assert v2.tolist() == [a & int(b) for a, b in zip(ov, sel)]
+    empty = ctx.logo_scan(sw, sh, 12)
+    assert empty.get_logo(255) is None                       # "Insufficient logo frames"
+
+
+def test_erase_logo_matches_oracle(ctx, oracle):
+    po = oracle
+    lg, P, O = _logos(po)
+    n = 6
+    fr = synth.make_frames(60, n, W, H, device="cuda", logo=lg, imgx=IMGX, imgy=IMGY)
+    work = fr.clone()
+    fades = np.array([[1.0, 1.0], [0.0, 0.0], [0.5, 0.5], [0.3, 0.7], [1.0, 0.0], [0.25, 0.25]], np.float32)
+    ctx.erase_logo(_clip(work, W, H), P["raw"], fades)
+    got = work.cpu().numpy()
+    ref = fr.cpu().numpy().copy()
+    for i in range(n):
+        Y, U, V = [np.ascontiguousarray(p[i]) for p in synth.split_planes(ref, W, H)]
+        po.or_erase_frame(O["raw"], Y, U, V, fades[i, 0], fades[i, 1])
+        exp = np.concatenate([Y.ravel(), U.ravel(), V.ravel()])
+        assert np.array_equal(got[i], exp), i
+    assert np.array_equal(got[1], fr.cpu().numpy()[1])       # fade 0 leaves the frame untouched
+    assert not np.array_equal(got[0], fr.cpu().numpy()[0])
+
+
+@pytest.mark.timeout(600)
+def test_full_size_properties_1080p(ctx, oracle):
+    """BASELINE-size frames (1920x1080): spot parity on a few frames + size-independent properties."""
+    po = oracle
+    w, h, n, imgx, imgy = 1920, 1080, 40, 1700, 60
+    lg = synth.make_logo(64, 64)
+    fr = torch.empty((n, w * h * 3 // 2), dtype=torch.uint8, device="cuda")
+    for n0 in range(0, n, 10):
+        synth.make_frames(100 + n0, 10, w, h, device="cuda", logo=lg, imgx=imgx, imgy=imgy, logo_period=30, out=fr[n0:n0 + 10])
+    clip = _clip(fr, w, h)
+    logo = ab.Logo.create(lg["data"], 64, 64, w, h, imgx, imgy).deint().create_mask(0.35)
+    prm = ab.default_comb_params()
+    s, c = ctx.scan_comb_frames(clip, [logo], prm)
+    s, c = s.cpu().numpy(), c.cpu().numpy()
+    o = po.OracleLogo.create(lg["data"], 64, 64, w, h, imgx, imgy).deint().create_mask(0.35)
+    Y, U, V = synth.split_planes(fr, w, h)
+    for i in (0, 1, 17, 39):
+        assert np.array_equal(_bits(s[i, 0]), _bits(o.scan_frame(Y[i])))
+        j = max(i - 1, 0)
+        assert np.array_equal(c[i], po.or_comb_frame((Y[i], U[i], V[i]), (Y[j], U[j], V[j]), prm.as_list()))
+    # properties: counters bounded by the number of pixels of their field; lshima <= shima; frame 0 has no motion
+    top_y = (h // 2) * w
+    assert (c[:, [0, 1, 2, 3, 4, 5]] <= top_y).all() and (c[:, 2] <= c[:, 1]).all() and (c[:, 5] <= c[:, 4]).all()
+    assert c[0, [0, 3, 6, 9]].sum() == 0
+    # split / merge invariance (range sharding with halo) and determinism
+    a = ctx.comb_frames(clip, prm, 0, 13).cpu().numpy()
+    b = ctx.comb_frames(clip, prm, 13, 27).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b]), c)
+    s2, c2 = ctx.scan_comb_frames(clip, [logo], prm)
+    assert np.array_equal(s2.cpu().numpy().view(np.uint32), s.view(np.uint32)) and np.array_equal(c2.cpu().numpy(), c)
+    assert s[:, 0, 0].max() > 0.8 and s[:, 0, 0].min() < 0.2

@@ -1,0 +1,158 @@
+"""CPU tests of the checker itself: the plain-C oracle (oracle/amtk_oracle.c) must reproduce
+  (1) the committed golden vectors the REFERENCE'S OWN code produced (tests/golden/logo_golden.json), always;
+  (2) the reference's own compiled code (oracle/_ref) live, when that library is present.
+All float comparisons are on bit patterns."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from amatsukaze_b200 import synth
+from oracle import pyoracle as po
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "logo_golden.json")))
+W, H, IMGX, IMGY = 256, 128, 160, 32
+needs_ref = pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32).ravel().tolist()
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def data():
+    lg = synth.make_logo(64, 64, seed=1)
+    frames = synth.make_frames(40, 24, W, H, seed=0x5EED0001, logo=lg, imgx=IMGX, imgy=IMGY, logo_period=20).numpy()
+    raw = po.OracleLogo.create(lg["data"], 64, 64, W, H, IMGX, IMGY)
+    logos = {"raw": raw, "deint": raw.deint().create_mask(0.35), "top": raw.field(0).create_mask(0.35),
+             "bot": raw.field(1).create_mask(0.35), "deint10": raw.deint().create_mask(0.1)}
+    return lg, frames, logos
+
+
+def test_corr5x5_avx_tree_matches_golden():
+    g = GOLD["corr5x5"]
+    rng = np.random.default_rng(g["seed"])
+    Y = np.concatenate([(rng.random(20 * 20) * 255).astype(np.float32), np.zeros(8, np.float32)])
+    K = np.concatenate([rng.standard_normal(25).astype(np.float32), np.zeros(8, np.float32)])
+    L = po.oracle_lib()
+    sums, avgs, scalar = [], [], []
+    for y in range(2, 18):
+        for x in range(2, 18):
+            a = C.c_float()
+            sums.append(L.amtk_or_corr5x5(K.ctypes.data_as(po.c_float_p), Y.ctypes.data_as(po.c_float_p), x, y, 20, C.byref(a)))
+            avgs.append(a.value)
+            scalar.append(L.amtk_or_corr5x5_scalar_order(K.ctypes.data_as(po.c_float_p), Y.ctypes.data_as(po.c_float_p), x, y, 20, None))
+    assert bits(sums) == g["sum_bits"] and bits(avgs) == g["avg_bits"]
+    # the scalar summation order is NOT what the reference runs on AVX hosts and differs in the last bits
+    assert bits(scalar) != g["sum_bits"]
+    assert np.allclose(scalar, sums, rtol=2e-3, atol=1e-2)
+
+
+def test_tables_match_golden(data):
+    _, _, logos = data
+    for name, t in GOLD["tables"].items():
+        l = logos[name]
+        ny = l.s.w * l.s.h
+        assert l.s.maskpixels == t["maskpixels"] and l.s.count == t["count"]
+        assert bits([l.s.blackScore])[0] == t["black_bits"]
+        assert digest(l.data()[:2 * ny]) == t["ab_sha"]
+        assert digest(l.mask()) == t["mask_sha"]
+        assert digest(l.kernels()) == t["kernels_sha"]
+        assert digest(l.scales()) == t["scales_sha"]
+
+
+def test_scan_and_analyze_match_golden(data):
+    _, frames, logos = data
+    Y, _, _ = synth.split_planes(frames, W, H)
+    for i in range(frames.shape[0]):
+        assert bits(logos["deint"].scan_frame(Y[i])) == GOLD["scan_frame_bits"][i]
+    for k, i in enumerate(GOLD["analyze_frames"]):
+        assert bits(po.or_analyze_frame(logos["deint"], logos["top"], logos["bot"], Y[i])) == GOLD["analyze_bits"][k]
+    on = np.array([np.array(b, np.uint32).view(np.float32)[0] for b in GOLD["scan_frame_bits"]])
+    assert on.max() > 0.8 and on.min() < 0.2          # the fixture covers logo present AND absent
+
+
+def test_fade_sweep_matches_golden(data):
+    _, frames, logos = data
+    Y, _, _ = synth.split_planes(frames, W, H)
+    de = np.zeros(64 * 64 + 8, np.float32)
+    roi = np.ascontiguousarray(Y[12])
+    po.oracle_lib().amtk_or_deint_y_u8(de.ctypes.data_as(po.c_float_p), roi.reshape(-1)[IMGX + IMGY * W:].ctypes.data_as(po.c_u8_p), W, 64, 64)
+    got = [logos["deint10"].evaluate(de, 255.0, np.float32(0.1) * np.float32(fi)) for fi in range(20)]
+    assert bits(got) == GOLD["fade_sweep_bits"]
+
+
+def test_logoscan_matches_golden():
+    flat = synth.make_frames(0, 40, 128, 96, seed=0x5EED0004, mode="flat", logo=synth.make_logo(32, 32, seed=3), imgx=64, imgy=32).numpy()
+    fy, fu, fv = synth.split_planes(flat, 128, 96)
+    sc = po.OracleScan(32, 32, 12)
+    valid = [sc.add_frame(fy[i][32:64, 64:96], fu[i][16:32, 32:48], fv[i][16:32, 32:48]) for i in range(flat.shape[0])]
+    g = GOLD["scan"]
+    assert valid == g["valid"] and sc.nframes == g["nframes"] and 0 < sc.nframes < len(valid)
+    assert digest(sc.sums()) == g["sums_sha"]
+    lg = sc.get_logo(255, clean=False)
+    assert digest(lg) == g["logo_sha"] and bits(lg[:16]) == g["logo_head_bits"]
+    assert digest(sc.get_logo(255, clean=True)) == g["logo_clean_sha"]
+
+
+def test_logoscan_insufficient_frames_returns_none():
+    sc = po.OracleScan(16, 16, 12)
+    assert sc.get_logo(255) is None      # 0 frames -> NaN slopes -> the reference returns nullptr (LogoScan.hpp:391,503)
+
+
+@needs_ref
+def test_oracle_equals_reference_live():
+    """Random logos / frames beyond the golden set, incl. 16-bit samples, odd sizes and a logo whose mask
+    spills into zero-variance pixels (count < maskpixels)."""
+    rng = np.random.default_rng(7)
+    for case, (w, h, ratio, bitsps) in enumerate(((64, 64, 0.35, 8), (48, 40, 0.9, 8), (64, 32, 0.35, 10), (32, 64, 0.1, 8))):
+        lg = synth.make_logo(w, h, seed=case)
+        data = lg["data"].copy()
+        if case == 1:
+            data[: w * h][(rng.random(w * h) < 0.3)] *= 1.0      # keep flat areas: high maskratio forces border picks
+        fw, fh, ix, iy = 320, 200, 100, 60
+        r = po.RefLogo.create(data, w, h, fw, fh, ix, iy).deint().create_mask(ratio)
+        o = po.OracleLogo.create(data, w, h, fw, fh, ix, iy).deint().create_mask(ratio)
+        assert r.visited_count() == o.s.count and r.dims()["maskpixels"] == o.s.maskpixels
+        assert np.array_equal(r.mask(), o.mask())
+        assert np.array_equal(r.kernels().view(np.uint32), o.kernels().view(np.uint32))
+        assert np.array_equal(r.scales().view(np.uint32), o.scales().view(np.uint32))
+        assert bits([r.black_score()]) == bits([o.s.blackScore])
+        maxv = float((1 << bitsps) - 1)
+        for _ in range(4):
+            if bitsps == 8:
+                plane = rng.integers(16, 236, (fh, fw), dtype=np.uint8)
+            else:
+                plane = rng.integers(64, 940, (fh, fw)).astype(np.uint16)
+            assert bits(po.ref_scan_frame(r, plane, maxv)) == bits(o.scan_frame(plane, maxv=maxv))
+        if case == 1:
+            assert o.s.count < o.s.maskpixels          # the quirk case really happened
+
+
+@needs_ref
+def test_oracle_logoscan_equals_reference_live():
+    rng = np.random.default_rng(11)
+    ro, oo = po.RefScan(24, 16, 10), po.OracleScan(24, 16, 10)
+    for i in range(60):
+        base = int(rng.integers(30, 200))
+        y = (base + rng.integers(-3, 4, (16, 24))).astype(np.uint8)
+        if i % 7 == 0:
+            y[0, 3] = 255                               # breaks the flat-border test
+        u = (128 + rng.integers(-2, 3, (8, 12))).astype(np.uint8)
+        v = (128 + rng.integers(-2, 3, (8, 12))).astype(np.uint8)
+        y[4:12, 6:18] = np.clip(y[4:12, 6:18].astype(int) + 40, 0, 255).astype(np.uint8)
+        assert ro.add_frame(y, u, v) == oo.add_frame(y, u, v)
+    assert ro.nframes == oo.nframes
+    assert np.array_equal(ro.sums(), oo.sums())
+    for clean in (False, True):
+        a, b = ro.get_logo(255, clean), oo.get_logo(255, clean)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
