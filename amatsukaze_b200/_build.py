@@ -55,5 +55,23 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_TEST = os.path.join(PKG, "..", "tests", "cpp", "test_filters")
+
+
+def build_host_test(force=False):
+    """tests/cpp/test_filters: the C++ driver of the host-side filter mirror (amatsukaze_b200/host/*.h*)."""
+    src = os.path.join(PKG, "..", "tests", "cpp", "test_filters.cpp")
+    deps = [src, os.path.join(PKG, "host", "filters.hpp"), os.path.join(PKG, "host", "avs_compat.h"), LIB]
+    if (not force and os.path.exists(HOST_TEST) and all(os.path.getmtime(HOST_TEST) >= os.path.getmtime(d) for d in deps)):
+        return HOST_TEST
+    cmd = ["g++", "-std=c++17", "-O2", "-o", HOST_TEST, src, "-L" + LIBDIR, "-lamtk_b200",
+           "-Wl,-rpath,$ORIGIN/../../amatsukaze_b200/lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("host test build failed")
+    return HOST_TEST
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -56,6 +56,10 @@ SIGNATURES = [
     ("amtk_ctx_get_kernel_timing", C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     ("amtk_host_alloc", C.c_int, [C.c_size_t, VP]),
     ("amtk_host_free", None, [V]),
+    ("amtk_device_alloc", C.c_int, [V, C.c_size_t, VP]),
+    ("amtk_device_free", None, [V, V]),
+    ("amtk_memcpy_h2d", C.c_int, [V, V, V, C.c_size_t]),
+    ("amtk_memcpy_d2h", C.c_int, [V, V, V, C.c_size_t]),
     ("amtk_logo_create", C.c_int, [V, c_float_p] + [C.c_int] * 8 + [VP]),
     ("amtk_logo_load", C.c_int, [V, C.c_char_p, VP, V]),
     ("amtk_logo_save", C.c_int, [V, C.c_char_p, C.c_char_p, C.c_int]),

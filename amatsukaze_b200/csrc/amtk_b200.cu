@@ -422,6 +422,33 @@ int amtk_host_alloc(size_t bytes, void** out) {
 }
 void amtk_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+int amtk_device_alloc(amtk_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) AMTK_FAIL("amtk_device_alloc: null argument");
+  DevSelect ds(c); if (!ds.ok) return 0;
+  AMTK_CUDA(cudaMalloc(out, bytes));
+  return 1;
+}
+void amtk_device_free(amtk_ctx* c, void* p) {
+  if (!c || !p) return;
+  DevSelect ds(c);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(p);
+}
+int amtk_memcpy_h2d(amtk_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c || !dst || !src) AMTK_FAIL("amtk_memcpy_h2d: null argument");
+  DevSelect ds(c); if (!ds.ok) return 0;
+  AMTK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  AMTK_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+int amtk_memcpy_d2h(amtk_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c || !dst || !src) AMTK_FAIL("amtk_memcpy_d2h: null argument");
+  DevSelect ds(c); if (!ds.ok) return 0;
+  AMTK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  AMTK_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // logos
 // ---------------------------------------------------------------------------------------------------------

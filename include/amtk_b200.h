@@ -52,6 +52,12 @@ AMTK_API int amtk_ctx_get_kernel_timing(amtk_ctx* ctx, double* ms_total, int64_t
 /* Pinned host memory for the host-buffer entry points (optional; pageable memory works, only slower). */
 AMTK_API int amtk_host_alloc(size_t bytes, void** out);
 AMTK_API void amtk_host_free(void* p);
+/* HBM buffers for device-resident clips (what AMTSource keeps its decoded frames in, replacing the reference's CPU
+ * frame cache, AMTSource.hpp:419-425) and synchronous copies on the context's stream. */
+AMTK_API int amtk_device_alloc(amtk_ctx* ctx, size_t bytes, void** out);
+AMTK_API void amtk_device_free(amtk_ctx* ctx, void* p);
+AMTK_API int amtk_memcpy_h2d(amtk_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
+AMTK_API int amtk_memcpy_d2h(amtk_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
 
 /* ---------------------------------------------------------------------------------------------
  * Clip descriptor: a run of planar YUV frames, either resident in HBM or in host memory.

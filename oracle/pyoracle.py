@@ -386,10 +386,24 @@ def ref_lib():
         R.ref_scan_normalize.argtypes = [V, C.c_int]
         R.ref_scan_get_logo.restype = C.c_int
         R.ref_scan_get_logo.argtypes = [V, C.c_int, c_float_p]
+        R.ref_logoframe_write.restype = C.c_int
+        R.ref_logoframe_write.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int), c_float_p]
         R.ref_bench_scan_comb_u8.restype = C.c_double
         R.ref_bench_scan_comb_u8.argtypes = [V, c_u8_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int, c_float_p, c_i32_p]
         _ref = R
     return _ref
+
+
+def ref_logoframe(eval_results, frames_per_sec, outpath=None, num_candidates=-1):
+    """The reference's LogoFrame::selectLogo (+ writeResult when outpath is given) on an (N, L, 2) score array.
+    Returns (bestLogo, logoRatio)."""
+    e = _f32(eval_results)
+    n, nl = e.shape[0], e.shape[1]
+    best, ratio = C.c_int(), C.c_float()
+    ok = ref_lib().ref_logoframe_write(_p(e, c_float_p), n, nl, frames_per_sec, num_candidates,
+                                       outpath.encode() if outpath else None, C.byref(best), C.byref(ratio))
+    assert ok
+    return best.value, ratio.value
 
 
 def cpu_scan_comb(frames, w, h, logo_data, imgx, imgy, th6, nthreads, maskratio=0.35, logo_w=64, logo_h=64):

@@ -20,6 +20,29 @@
 
 using namespace logo;
 
+/* ---- LogoFrame::selectLogo / writeResult (LogoScan.hpp:1645-1827), verbatim inside a shim class that only supplies
+ * the members those two functions touch (numLogos, evalResults, numFrames, framesPerSec, bestLogo, logoRatio, ctx). */
+#include <cstdarg>
+struct RefCtxShim { void debugF(const char*, ...) {} };
+class StringBuilder {
+  std::string s_;
+public:
+  template <typename... Args> StringBuilder& append(const char* fmt, Args const&... args) {
+    char buf[256]; snprintf(buf, sizeof(buf), fmt, args...); s_ += buf; return *this;
+  }
+  MemoryChunk getMC() { return MemoryChunk((uint8_t*)s_.data(), s_.size()); }
+};
+struct RefLogoFrame {
+  RefCtxShim ctx;
+  int numLogos = 0, numFrames = 0, framesPerSec = 30;
+  struct EvalResult { float corr0, corr1; };
+  std::unique_ptr<EvalResult[]> evalResults;
+  const float THRESH = 0.2f;
+  int bestLogo = -1;
+  float logoRatio = 0;
+#include "ref_logoframe.inc"
+};
+
 extern "C" {
 
 /* ---- ComputeKernel.cpp / LogoScan.hpp:24-41 ---- */
@@ -141,6 +164,22 @@ int ref_scan_get_logo(void* p, int clean, float* out) {
   size_t n = (size_t)(s->scanw * s->scanh + (s->scanw >> s->logUVx) * (s->scanh >> s->logUVy) * 2) * 2;
   memcpy(out, d->data.get(), n * sizeof(float));
   return 1;
+}
+
+/* ---- LogoFrame post-processing ---- */
+int ref_logoframe_write(const float* eval /* [numFrames][numLogos][2] */, int numFrames, int numLogos, int framesPerSec,
+                        int numCandidates, const char* outpath, int* bestLogo, float* logoRatio) {
+  try {
+    RefLogoFrame lf;
+    lf.numLogos = numLogos; lf.numFrames = numFrames; lf.framesPerSec = framesPerSec;
+    lf.evalResults.reset(new RefLogoFrame::EvalResult[(size_t)numFrames * numLogos]);
+    memcpy(lf.evalResults.get(), eval, sizeof(float) * 2 * (size_t)numFrames * numLogos);
+    lf.selectLogo(numCandidates);
+    if (bestLogo) *bestLogo = lf.bestLogo;
+    if (logoRatio) *logoRatio = lf.logoRatio;
+    if (outpath) lf.writeResult(outpath);
+    return 1;
+  } catch (const IOException&) { return 0; }
 }
 
 /* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline leg) ----------------------------
