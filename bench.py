@@ -190,17 +190,17 @@ def main():
     clip_t = make_clip(torch, synth, logo_def, device, SEED + rank)
     torch.cuda.synchronize()
     clip = ab.yv12_clip(clip_t, W, H, CLIP_FRAMES, on_device=True)
-    scores = torch.empty((CLIP_FRAMES, 1, 2), dtype=torch.float32, device=device)
-    counts = torch.empty((CLIP_FRAMES, 12), dtype=torch.int32, device=device)
-    if world > 1:
-        g_scores = torch.empty((world * CLIP_FRAMES, 1, 2), dtype=torch.float32, device=device)
-        g_counts = torch.empty((world * CLIP_FRAMES, 12), dtype=torch.int32, device=device)
+    # per-frame results of one pass live back to back in ONE buffer so that the final gather is a single collective
+    results = torch.empty(CLIP_FRAMES * (2 + 12), dtype=torch.int32, device=device)
+    scores = results[: CLIP_FRAMES * 2].view(torch.float32).view(CLIP_FRAMES, 1, 2)
+    counts = results[CLIP_FRAMES * 2:].view(CLIP_FRAMES, 12)
+    from amatsukaze_b200 import shard
+    gathered = {}
 
     def step():
         ctx.scan_comb_frames(clip, [logo], prm, scores=scores, counts=counts)
-        if world > 1:      # final score gather of the pass (NCCL over NVLink; ~100 KB per rank)
-            dist.all_gather_into_tensor(g_scores, scores)
-            dist.all_gather_into_tensor(g_counts, counts)
+        if world > 1:      # final score gather of the pass (NCCL over NVLink; ~100 KB per rank, no other traffic)
+            gathered["results"] = shard.gather_streams(results)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
