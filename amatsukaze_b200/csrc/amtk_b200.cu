@@ -122,8 +122,30 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     AMTK_FAIL("logo has no feature pixels");
   }
   const int countPad = sp.logo->countPad;
-  const size_t smem = logo_scores_smem_bytes(sp.roi_w * sp.roi_h, hl.w * hl.h, clip->bytes_per_sample);
+  // ROI staging: TMA box of (roi_w rounded up to 16 bytes) x roi_h samples per frame, when the layout allows it
+  const int bps = clip->bytes_per_sample;
+  // the box starts at imgx rounded down to 16 bytes: the TMA unit raises "illegal instruction" when the innermost
+  // start address is not 16-byte aligned (measured on B200; tools/tma_align_probe.py)
+  const int box_x = ((sp.roi_x * bps) & ~15) / bps;
+  const int box_w = ((((sp.roi_x - box_x) + sp.roi_w) * bps + 15) & ~15) / bps;
+  const long long pitch_bytes = (long long)pitch_elems * bps;
+  const long long plane_rows = ((long long)clip->pitch_y * clip->height) / pitch_bytes;     // rows as addressed with pitch_elems
+  const bool tma_ok = ctx->encode_tiled && box_w <= 256 && sp.roi_h <= 256 && (pitch_bytes & 15) == 0 &&
+                      (clip->frame_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(win.dev_base) & 15) == 0;
+  const size_t smem = logo_scores_smem_bytes(sp.roi_w * sp.roi_h, hl.w * hl.h, box_w * sp.roi_h * bps);
   if (smem > 200 * 1024) AMTK_FAIL("logo too large for the shared-memory evaluation path");
+  CUtensorMap roi_map;
+  memset(&roi_map, 0, sizeof(roi_map));
+  if (tma_ok) {
+    cuuint64_t gdim[3] = { (cuuint64_t)pitch_elems, (cuuint64_t)plane_rows, (cuuint64_t)win.count };
+    cuuint64_t gstr[2] = { (cuuint64_t)pitch_bytes, (cuuint64_t)clip->frame_stride };
+    cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)sp.roi_h, 1u };
+    cuuint32_t estr[3] = { 1u, 1u, 1u };
+    CUresult r = ctx->encode_tiled(&roi_map, bps == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3,
+                                   const_cast<uint8_t*>(win.dev_base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) AMTK_FAIL("cuTensorMapEncodeTiled(roi) failed (" + std::to_string((int)r) + ")");
+  }
   // frames per launch bounded by the score scratch (<= 96 MB)
   const size_t per_frame = (size_t)sp.nfades * countPad * sizeof(float);
   const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)(hi - lo), ((size_t)96 << 20) / per_frame));
@@ -139,6 +161,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     job.logo = logo_dev(sp.logo); job.maxv = maxv; job.nfades = sp.nfades;
     for (int i = 0; i < sp.nfades; ++i) job.fades[i] = sp.fades[i];
     job.scores = reinterpret_cast<float*>(ctx->scratch);
+    job.use_tma = tma_ok ? 1 : 0; job.roi_box_w = box_w; job.roi_box_x = box_x; job.roi_map = roi_map;
     const int slices3 = (count + kEvalThreads * 3 - 1) / (kEvalThreads * 3);
     int pxt = 3, slices = slices3;
     if (count <= kEvalThreads) { pxt = 1; slices = 1; }

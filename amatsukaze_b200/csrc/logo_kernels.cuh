@@ -17,6 +17,7 @@
 #pragma once
 #include "amtk_internal.h"
 #include "exact_math.h"
+#include "tma_utils.cuh"
 
 namespace amtk {
 
@@ -37,23 +38,26 @@ struct EvalJob {
   int nfades;
   float fades[kMaxFades];
   float* scores;             // [nframes][nfades][countPad]
+  int use_tma;               // 1: the ROI is fetched by TMA through roi_map (box roi_box_w x roi_h x 1 elements)
+  int roi_box_w;             // row pitch of the staged raw ROI in ELEMENTS (multiple of 16 bytes)
+  int roi_box_x;             // x of the box in the frame: imgx rounded DOWN to 16 bytes (TMA faults on unaligned starts)
+  CUtensorMap roi_map;       // 3-D (x, y, frame) view of the Y plane as addressed with `pitch`
 };
 
 // Shared-memory layout of logo_scores_kernel (floats unless noted):
 //   A[npx] B[npx]      logo planes, loaded once per CTA
 //   src[roi_n]         the frame's ROI as float (DeintY or CopyY)
 //   work[npx + 8]      logo-removed image of the current fade
-//   raw[roi_n]         pixel_t: the ROI bytes of the NEXT frame of this CTA (register-prefetched, then staged)
-__host__ __device__ inline size_t logo_scores_smem_bytes(int roi_n, int npx, int bytes_per_sample) {
-  return ((size_t)2 * ((npx + 3) & ~3) + ((roi_n + 3) & ~3) + (size_t)npx + 8) * sizeof(float) +
-         (((size_t)roi_n * bytes_per_sample + 15) & ~(size_t)15);
+//   raw[2][box_w*roi_h] pixel_t: double-buffered ROI samples, filled by TMA one frame ahead (128-byte aligned)
+__host__ __device__ inline size_t logo_scores_smem_bytes(int roi_n, int npx, int raw_bytes_one) {
+  return ((size_t)2 * ((npx + 3) & ~3) + ((roi_n + 3) & ~3) + (((size_t)npx + 8 + 3) & ~(size_t)3)) * sizeof(float) +
+         128 + 2 * (((size_t)raw_bytes_one + 127) & ~(size_t)127);
 }
 
-constexpr int kRoiPrefetch = 8;    // ROI elements per thread held in registers for the next frame (ROIs up to 4096 px)
-
 template <typename pixel_t, int PXT>
-__global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const EvalJob job) {
+__global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __grid_constant__ EvalJob job) {
   extern __shared__ float smem_f[];
+  __shared__ __align__(8) uint64_t roi_bar[2];
   const int tid = threadIdx.x;
   const LogoDev& lg = job.logo;
   const int w = lg.w, npx = lg.w * lg.h;
@@ -62,7 +66,11 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const Eval
   float* sB = sA + ((npx + 3) & ~3);
   float* src = sB + ((npx + 3) & ~3);
   float* work = src + ((roi_n + 3) & ~3);
-  pixel_t* raw = reinterpret_cast<pixel_t*>(work + npx + 8);
+  uint8_t* raw_base = reinterpret_cast<uint8_t*>(work + ((npx + 8 + 3) & ~3));
+  raw_base += (128u - (smem_u32(raw_base) & 127u)) & 127u;
+  const int raw_pitch = job.roi_box_w;                                   // elements per staged ROI row
+  const uint32_t raw_bytes = (uint32_t)raw_pitch * job.roi_h * sizeof(pixel_t);
+  const uint32_t raw_stride = (raw_bytes + 127u) & ~127u;
 
   // ---- one-time: logo planes to smem, adopt feature pixels, pull their taps into registers ----
   for (int i = tid; i < npx; i += kEvalThreads) { sA[i] = lg.A[i]; sB[i] = lg.B[i]; }
@@ -89,51 +97,50 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const Eval
   const int roi_y0 = tid / job.roi_w, roi_x0 = tid - roi_y0 * job.roi_w;
   const int lg_dx = kEvalThreads % w, lg_dy = kEvalThreads / w;
   const int lg_y0 = tid / w, lg_x0 = tid - lg_y0 * w;
-  const bool prefetch_ok = roi_n <= kRoiPrefetch * kEvalThreads;
 
-  auto roi_ptr = [&](int f) {
-    const pixel_t* fr = reinterpret_cast<const pixel_t*>(
-        reinterpret_cast<const uint8_t*>(job.ybase) + (long long)(job.frame0 + f) * job.frame_stride);
-    return fr + job.imgx + (long long)job.imgy * job.pitch;
-  };
-  pixel_t pre[kRoiPrefetch];
-  auto fetch = [&](int f) {         // coalesced element loads of the frame's ROI into registers
-    const pixel_t* roi = roi_ptr(f);
-    int x = roi_x0, y = roi_y0;
-#pragma unroll
-    for (int k = 0; k < kRoiPrefetch; ++k) {
-      if (tid + k * kEvalThreads < roi_n) pre[k] = roi[x + (long long)y * job.pitch];
-      x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
-    }
-  };
-  int f = blockIdx.y;
-  if (prefetch_ok && f < job.nframes) fetch(f);
+  if (job.use_tma && tid == 0) {
+    mbar_init(&roi_bar[0], 1); mbar_init(&roi_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  for (; f < job.nframes; f += gridDim.y) {
-    // ---- stage the ROI bytes (prefetched registers, or direct loads for very large ROIs) ----
-    if (prefetch_ok) {
-#pragma unroll
-      for (int k = 0; k < kRoiPrefetch; ++k) if (tid + k * kEvalThreads < roi_n) raw[tid + k * kEvalThreads] = pre[k];
-    } else {
-      const pixel_t* roi = roi_ptr(f);
+  auto issue_roi = [&](int f, int buf) {          // thread 0: TMA box (roi_box_w x roi_h) of frame f -> raw[buf]
+    mbar_expect_tx(&roi_bar[buf], raw_bytes);
+    tma_load_3d(raw_base + buf * raw_stride, &job.roi_map, &roi_bar[buf], job.roi_box_x, job.imgy, job.frame0 + f);
+  };
+  float pend_sum[PXT]; float2 pend_sc[PXT]; float* pend_out = nullptr;     // evaluation whose scores are still owed
+  int f = blockIdx.y;
+  if (job.use_tma && tid == 0 && f < job.nframes) issue_roi(f, 0);
+  for (int it = 0; f < job.nframes; f += gridDim.y, ++it) {
+    const pixel_t* raw;
+    if (job.use_tma) {
+      // the other buffer was last read in the previous iteration, before several block barriers: free to refill
+      if (tid == 0 && f + (int)gridDim.y < job.nframes) issue_roi(f + gridDim.y, (it + 1) & 1);
+      mbar_wait(&roi_bar[it & 1], (uint32_t)(it >> 1) & 1u);
+      raw = reinterpret_cast<const pixel_t*>(raw_base + (it & 1) * raw_stride) + (job.imgx - job.roi_box_x);
+    } else {                                       // layouts TMA cannot describe: plain coalesced element loads
+      const pixel_t* fr = reinterpret_cast<const pixel_t*>(
+          reinterpret_cast<const uint8_t*>(job.ybase) + (long long)(job.frame0 + f) * job.frame_stride);
+      const pixel_t* roi = fr + job.imgx + (long long)job.imgy * job.pitch;
+      pixel_t* dst = reinterpret_cast<pixel_t*>(raw_base);
       int x = roi_x0, y = roi_y0;
       for (int i = tid; i < roi_n; i += kEvalThreads) {
-        raw[i] = roi[x + (long long)y * job.pitch];
+        dst[x + y * raw_pitch] = roi[x + (long long)y * job.pitch];
         x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
       }
+      __syncthreads();
+      raw = dst;
     }
-    __syncthreads();
-    if (prefetch_ok && f + (int)gridDim.y < job.nframes) fetch(f + gridDim.y);   // in flight during this frame's math
     // ---- ROI as float: DeintY (:763-780) or CopyY (:782-790) ----
     {
       int x = roi_x0, y = roi_y0;
       for (int i = tid; i < roi_n; i += kEvalThreads) {
+        const pixel_t* rp = raw + x + y * raw_pitch;
         float v;
         if (job.src_mode == 0 && y > 0 && y < job.roi_h - 1) {
-          const int a = raw[i - job.roi_w], b = raw[i], c = raw[i + job.roi_w];
+          const int a = rp[-raw_pitch], b = rp[0], c = rp[raw_pitch];
           v = (float)(a + 2 * b + c + 2) / 4.0f;       // exact: integer < 2^24, division by 4
         } else {
-          v = (float)raw[i];
+          v = (float)rp[0];
         }
         src[i] = v;
         x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
@@ -154,25 +161,29 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const Eval
         }
       }
       __syncthreads();
-      // ---- per-feature score (LogoScan.hpp:298-308) ----
-      float* out = job.scores + ((size_t)f * job.nfades + fi) * lg.countPad;
-      float sums[PXT]; int bins[PXT];
+      // ---- per-feature score (LogoScan.hpp:298-308), software-pipelined across evaluations: the scale-table
+      // gather of THIS evaluation (data dependent through avg) is only consumed after the next evaluation's image
+      // has been built, so its L2/DRAM latency hides behind that work instead of stalling all 16 warps ----
+      if (pend_out) {
+#pragma unroll
+        for (int p = 0; p < PXT; ++p)
+          if (cidx[p] < lg.count) pend_out[cidx[p]] = pixel_score(pend_sum[p], pend_sc[p].x, pend_sc[p].y);
+      }
 #pragma unroll
       for (int p = 0; p < PXT; ++p) {
         const float* wp = work + pxy[p];
         float avg;
-        sums[p] = corr5x5_tree(taps[p], [&](int dy, int dx) { return wp[dy * w + dx]; }, &avg);
-        bins[p] = scale_bin(avg);
+        pend_sum[p] = corr5x5_tree(taps[p], [&](int dy, int dx) { return wp[dy * w + dx]; }, &avg);
+        pend_sc[p] = (cidx[p] < lg.count) ? __ldg(lg.scales + (size_t)cidx[p] * 32 + scale_bin(avg)) : make_float2(0.0f, 0.0f);
       }
-      float2 sc[PXT];
-#pragma unroll
-      for (int p = 0; p < PXT; ++p)      // all scale gathers in flight together
-        sc[p] = (cidx[p] < lg.count) ? __ldg(lg.scales + (size_t)cidx[p] * 32 + bins[p]) : make_float2(0.0f, 0.0f);
-#pragma unroll
-      for (int p = 0; p < PXT; ++p)
-        if (cidx[p] < lg.count) out[cidx[p]] = pixel_score(sums[p], sc[p].x, sc[p].y);
+      pend_out = job.scores + ((size_t)f * job.nfades + fi) * lg.countPad;
       __syncthreads();     // `work` is rewritten by the next fade / `src` by the next frame
     }
+  }
+  if (pend_out) {
+#pragma unroll
+    for (int p = 0; p < PXT; ++p)
+      if (cidx[p] < lg.count) pend_out[cidx[p]] = pixel_score(pend_sum[p], pend_sc[p].x, pend_sc[p].y);
   }
 }
 

@@ -276,3 +276,20 @@ def test_full_size_properties_1080p(ctx, oracle):
     s2, c2 = ctx.scan_comb_frames(clip, [logo], prm)
     assert np.array_equal(s2.cpu().numpy().view(np.uint32), s.view(np.uint32)) and np.array_equal(c2.cpu().numpy(), c)
     assert s[:, 0, 0].max() > 0.8 and s[:, 0, 0].min() < 0.2
+
+
+def test_scan_frames_unaligned_pitch_fallback(ctx, oracle):
+    """Row pitch not a multiple of 16 bytes: TMA cannot describe the plane, the kernel falls back to plain loads."""
+    po = oracle
+    w, h, imgx, imgy = 200, 96, 120, 20
+    lg = synth.make_logo(48, 40, seed=6)
+    p = ab.Logo.create(lg["data"], 48, 40, w, h, imgx, imgy).deint().create_mask(0.35)
+    o = po.OracleLogo.create(lg["data"], 48, 40, w, h, imgx, imgy).deint().create_mask(0.35)
+    n = 7
+    fr = synth.make_frames(20, n, w, h, device="cuda", logo=lg, imgx=imgx, imgy=imgy, logo_period=10)
+    out = ctx.scan_frames(_clip(fr, w, h), [p]).cpu().numpy()
+    Y, _, _ = synth.split_planes(fr, w, h)
+    ref = np.stack([o.scan_frame(Y[i]) for i in range(n)])
+    assert np.array_equal(_bits(out[:, 0]), _bits(ref))
+    with pytest.raises(ab.AmtkError, match="multiples of 16"):
+        ctx.comb_frames(_clip(fr, w, h))
