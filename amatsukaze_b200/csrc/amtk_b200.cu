@@ -179,9 +179,16 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
 #undef AMTK_LAUNCH_SCORES
     AMTK_CUDA(cudaGetLastError());
     const int total = n * sp.nfades;
-    logo_sum_kernel<<<(total + kSumThreads - 1) / kSumThreads, kSumThreads, 0, ctx->stream>>>(
-        job.scores, count, countPad, n, sp.nfades, hl.blackScore, sp.take_abs,
-        dout + (size_t)(f0 - out_row0) * out_frame_stride, out_frame_stride, sp.out_off, sp.out_fade_stride);
+    float* sum_out = dout + (size_t)(f0 - out_row0) * out_frame_stride;
+    const size_t sum_smem = (size_t)32 * (countPad + 4) * sizeof(float);
+    if (sum_smem <= 200 * 1024) {
+      AMTK_CUDA(cudaFuncSetAttribute(logo_sum_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
+      logo_sum_bulk_kernel<<<(total + 31) / 32, 32, sum_smem, ctx->stream>>>(
+          job.scores, count, countPad, n, sp.nfades, hl.blackScore, sp.take_abs, sum_out, out_frame_stride, sp.out_off, sp.out_fade_stride);
+    } else {
+      logo_sum_kernel<<<(total + kSumThreads - 1) / kSumThreads, kSumThreads, 0, ctx->stream>>>(
+          job.scores, count, countPad, n, sp.nfades, hl.blackScore, sp.take_abs, sum_out, out_frame_stride, sp.out_off, sp.out_fade_stride);
+    }
     AMTK_CUDA(cudaGetLastError());
     ctx->launches += 2;
   }

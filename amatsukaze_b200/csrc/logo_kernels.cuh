@@ -234,6 +234,44 @@ __global__ void __launch_bounds__(kSumThreads) logo_sum_kernel(const float* __re
   out[(size_t)f * out_frame_stride + out_off + (size_t)fi * out_fade_stride] = v;
 }
 
+// Same reduction with the 32 score rows of a warp brought into shared memory by 32 bulk copies (all in flight at
+// once, ~168 KB for a 64x64 logo), after which each lane walks its row with conflict-free LDS.128 (row pitch
+// countPad+4 floats = 4 banks apart per lane).  The dependent-add chain then runs at ALU latency instead of waiting
+// on a global load every 128 bytes.
+__global__ void __launch_bounds__(32) logo_sum_bulk_kernel(const float* __restrict__ scores, int count, int countPad,
+                                                            int nframes, int nfades, float blackScore, int take_abs,
+                                                            float* __restrict__ out, int out_frame_stride, int out_off,
+                                                            int out_fade_stride) {
+  extern __shared__ __align__(16) float sum_rows[];
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x, total = nframes * nfades;
+  const int t0 = blockIdx.x * 32, nrows = min(32, total - t0);
+  const int pitch = countPad + 4;
+  const uint32_t row_bytes = (uint32_t)countPad * sizeof(float);
+  if (lane == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncwarp();
+  if (lane == 0) mbar_expect_tx(&bar, row_bytes * (uint32_t)nrows);
+  __syncwarp();
+  if (lane < nrows) bulk_load_1d(sum_rows + (size_t)lane * pitch, scores + (size_t)(t0 + lane) * countPad, row_bytes, &bar);
+  mbar_wait(&bar, 0);
+  if (lane >= nrows) return;
+  const float4* row = reinterpret_cast<const float4*>(sum_rows + (size_t)lane * pitch);
+  float r = 0.0f;
+  const int n4 = count >> 2;
+#pragma unroll 8
+  for (int i = 0; i < n4; ++i) {
+    const float4 v = row[i];
+    r = AMTK_FADD(r, v.x); r = AMTK_FADD(r, v.y); r = AMTK_FADD(r, v.z); r = AMTK_FADD(r, v.w);
+  }
+  const float* tail = sum_rows + (size_t)lane * pitch;
+  for (int c = n4 << 2; c < count; ++c) r = AMTK_FADD(r, tail[c]);
+  float v = AMTK_FDIV(r, blackScore);
+  if (take_abs) v = fabsf(v);
+  const int t = t0 + lane;
+  const int f = t / nfades, fi = t - f * nfades;
+  out[(size_t)f * out_frame_stride + out_off + (size_t)fi * out_fade_stride] = v;
+}
+
 __global__ void fill_pairs_kernel(float* out, int nframes, int stride, int off, float v0, float v1) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f < nframes) { out[(size_t)f * stride + off] = v0; out[(size_t)f * stride + off + 1] = v1; }
