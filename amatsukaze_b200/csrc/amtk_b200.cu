@@ -206,7 +206,12 @@ static bool roi_inside(const amtk::HostLogo& full, const amtk_clip* clip, int pi
 // ---------------------------------------------------------------------------------------------------------
 // comb launch
 // ---------------------------------------------------------------------------------------------------------
-static int comb_thresholds_ok(const amtk_comb_params* p) {
+static int comb_thresholds_ok(const amtk_comb_params* p, int bytes_per_sample) {
+  if (bytes_per_sample == 2) {       // generic integer kernel: any positive threshold
+    const int all[6] = { p->th_move_y, p->th_shima_y, p->th_lshima_y, p->th_move_c, p->th_shima_c, p->th_lshima_c };
+    for (int v : all) if (v < 1) { set_error("comb: thresholds must be >= 1"); return 0; }
+    return 1;
+  }
   const int m[2] = { p->th_move_y, p->th_move_c };
   const int s[4] = { p->th_shima_y, p->th_lshima_y, p->th_shima_c, p->th_lshima_c };
   for (int v : m) if (v < 1 || v > 128) { set_error("comb: th_move must be in [1,128]"); return 0; }
@@ -230,17 +235,19 @@ static const CombVariant* comb_variants(int* n) {
     make_variant<CombCfg<17, 8, 4, 0>>(), make_variant<CombCfg<17, 8, 4, 1>>(), make_variant<CombCfg<17, 8, 4, 2>>(),
     make_variant<CombCfg<15, 8, 2, 0>>(), make_variant<CombCfg<16, 8, 2, 0>>(), make_variant<CombCfg<17, 8, 2, 0>>(),
     make_variant<CombCfg<17, 4, 2, 0>>(), make_variant<CombCfg<17, 4, 3, 0>>(),
+    make_variant<CombCfg<34, 8, 2, 0, 4>>(), make_variant<CombCfg<34, 8, 3, 0, 4>>(), make_variant<CombCfg<34, 8, 4, 0, 4>>(),
   };
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }
+static int g_comb_force_generic = 0;
 static int g_comb_strip = 8, g_comb_stages = 3, g_comb_R = 0, g_comb_ctas_per_sm = 0, g_comb_acc = 0, g_comb_l2 = 128;   // tuning knobs (env AMTK_COMB_*)
 
 // rows per run: the R in {15,16,17} that wastes the fewest rows over luma + chroma (1080/540 -> 17, 720/360 -> 15)
 static int pick_comb_R(int hY, int hC) {
   int best = 16; long long best_waste = -1;
   for (int R = 17; R >= 15; --R) {
-    const int th = kCombRuns * R;
+    const int th = 8 * R;
     const long long waste = (long long)((hY + th - 1) / th) * th - hY + 2LL * (((hC + th - 1) / th) * th - hC) / 2;
     if (best_waste < 0 || waste < best_waste) { best_waste = waste; best = R; }
   }
@@ -249,11 +256,37 @@ static int pick_comb_R(int hY, int hC) {
 
 static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi,
                        const amtk_comb_params* prm, int* dcounts, int out_row0) {
-  if (clip->bytes_per_sample != 1) AMTK_FAIL("comb: 16-bit samples are not supported by this build (YV12 only)");
-  if ((clip->frame_stride & 15) || (clip->pitch_y & 15) || (clip->pitch_uv & 15) || (clip->off_u & 15) || (clip->off_v & 15) ||
-      (reinterpret_cast<uintptr_t>(win.dev_base) & 15))
-    AMTK_FAIL("comb: base, frame_stride, plane offsets and pitches must be multiples of 16 bytes (TMA)");
-  if (!ctx->encode_tiled) AMTK_FAIL("cuTensorMapEncodeTiled unavailable (driver too old?)");
+  const bool tma_layout = !((clip->frame_stride & 15) || (clip->pitch_y & 15) || (clip->pitch_uv & 15) || (clip->off_u & 15) ||
+                            (clip->off_v & 15) || (reinterpret_cast<uintptr_t>(win.dev_base) & 15));
+  if (clip->bytes_per_sample != 1 || !tma_layout || !ctx->encode_tiled || g_comb_force_generic) {
+    // generic kernel: any sample size / pitch (DESIGN.md 3.1 "fallback")
+    CombGenericArgs g;
+    g.base = win.dev_base; g.frame_stride = clip->frame_stride;
+    g.off[0] = 0; g.off[1] = clip->off_u; g.off[2] = clip->off_v;
+    const int bps = clip->bytes_per_sample;
+    for (int pl = 0; pl < 3; ++pl) {
+      g.pitch[pl] = (pl ? clip->pitch_uv : clip->pitch_y) / bps;
+      g.W[pl] = pl ? (clip->width >> clip->log_uvx) : clip->width;
+      g.H[pl] = pl ? (clip->height >> clip->log_uvy) : clip->height;
+      g.thM[pl] = pl ? prm->th_move_c : prm->th_move_y;
+      g.thS[pl] = pl ? prm->th_shima_c : prm->th_shima_y;
+      g.thL[pl] = pl ? prm->th_lshima_c : prm->th_lshima_y;
+    }
+    g.first_frame = lo - win.first; g.prev_of_first = lo > 0 ? lo - 1 - win.first : lo - win.first;
+    g.nframes = hi - lo; g.counts = dcounts + (size_t)(lo - out_row0) * 12;
+    AMTK_CUDA(cudaMemsetAsync(g.counts, 0, (size_t)(hi - lo) * 12 * sizeof(int), ctx->stream));
+    for (int f0 = 0; f0 < hi - lo; f0 += 16384) {            // gridDim.z limit
+      CombGenericArgs gg = g;
+      gg.first_frame = g.first_frame + f0; gg.prev_of_first = f0 ? gg.first_frame - 1 : g.prev_of_first;
+      gg.nframes = std::min(16384, hi - lo - f0); gg.counts = g.counts + (size_t)f0 * 12;
+      dim3 grid((g.W[0] + 31) / 32, (g.H[0] + 7) / 8, gg.nframes * 3);
+      if (bps == 1) comb_generic_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(gg);
+      else comb_generic_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(gg);
+      AMTK_CUDA(cudaGetLastError());
+      ctx->launches += 1;
+    }
+    return 1;
+  }
   const int hY = clip->height, hC = clip->height >> clip->log_uvy;
   const int R = g_comb_R ? g_comb_R : pick_comb_R(hY, hC);
   int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
@@ -391,6 +424,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_R")) g_comb_R = atoi(e);
   if (const char* e = getenv("AMTK_COMB_CTAS")) g_comb_ctas_per_sm = atoi(e);
   if (const char* e = getenv("AMTK_COMB_ACC")) g_comb_acc = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_GENERIC")) g_comb_force_generic = atoi(e);
   if (const char* e = getenv("AMTK_COMB_L2")) g_comb_l2 = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }
@@ -722,7 +756,7 @@ void amtk_comb_default_params(amtk_comb_params* p) {
 int amtk_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_comb_params* prm, int frame0, int nframes,
                      int32_t* counts, int out_on_device) {
   if (!ctx || !prm || !counts) AMTK_FAIL("amtk_comb_frames: bad argument");
-  if (!validate_clip(clip, true) || !comb_thresholds_ok(prm)) return 0;
+  if (!validate_clip(clip, true) || !comb_thresholds_ok(prm, clip->bytes_per_sample)) return 0;
   DevSelect ds(ctx); if (!ds.ok) return 0;
   const size_t bytes = (size_t)nframes * 12 * sizeof(int32_t);
   int* d = counts;
@@ -736,7 +770,7 @@ int amtk_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_comb_param
 int amtk_scan_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
                           const amtk_comb_params* prm, int frame0, int nframes, float* scores, int32_t* counts, int out_on_device) {
   if (!ctx || !prm || !counts || !scores || !logos || nlogos < 1) AMTK_FAIL("amtk_scan_comb_frames: bad argument");
-  if (!validate_clip(clip, true) || !comb_thresholds_ok(prm)) return 0;
+  if (!validate_clip(clip, true) || !comb_thresholds_ok(prm, clip->bytes_per_sample)) return 0;
   DevSelect ds(ctx); if (!ds.ok) return 0;
   const size_t sbytes = (size_t)nframes * nlogos * 2 * sizeof(float), cbytes = (size_t)nframes * 12 * sizeof(int32_t);
   float* ds_ = scores; int* dc = counts;

@@ -29,19 +29,18 @@
 namespace amtk {
 
 constexpr int kCombTW = 128;            // tile width in bytes (= pixels for u8)
-constexpr int kCombRuns = 8;            // vertical runs per tile (one per half-warp / warp)
 
 // Compile-time shape of one kernel variant: R rows per run (tile height 8R), STRIP pixels per thread-row,
 // STAGES ring slots.
 // ACC selects how threshold hits are counted: 0 = integer masks + IADD3 (ALU pipe), 1 = lshima as fp16 1.0s +
 // HADD2 (FMA pipe), 2 = both numeric (pipe balancing knob; results are identical).
-template <int R_, int STRIP_, int STAGES_, int ACC_ = 0>
+template <int R_, int STRIP_, int STAGES_, int ACC_ = 0, int RUNS_ = 8>
 struct CombCfg {
-  static constexpr int R = R_, STRIP = STRIP_, STAGES = STAGES_, ACC = ACC_;
-  static constexpr int TH = kCombRuns * R;                 // output rows per tile
+  static constexpr int R = R_, STRIP = STRIP_, STAGES = STAGES_, ACC = ACC_, RUNS = RUNS_;   // RUNS vertical runs per tile
+  static constexpr int TH = RUNS * R;                      // output rows per tile
   static constexpr int BOXH = TH + 4;                      // with +-2 halo rows
   static constexpr int STAGE_BYTES = kCombTW * BOXH;
-  static constexpr int THREADS = (kCombTW / STRIP) * kCombRuns;
+  static constexpr int THREADS = (kCombTW / STRIP) * RUNS;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 128;  // + alignment slack
   static constexpr int NQ = STRIP / 2;                     // half2 per thread-row
 };
@@ -104,7 +103,8 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t d, uint32_t kM) {
 
 template <typename Cfg, bool EDGE>
 __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
-                                               int y_first /* global y of this thread's first row */, int H,
+                                               int y_first /* global y of this thread's first row */,
+                                               const uint32_t* __restrict__ th_rows /* EDGE: [2][R] thresholds of this run */,
                                                uint32_t kM, uint32_t thS_bits, uint32_t thL_bits,
                                                uint32_t& oS, uint32_t& oL, uint32_t& oM) {
   // cur/prev point at this thread's strip in smem row (run*R) of the box, i.e. global row y_first-2.
@@ -127,11 +127,12 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
     const HRow<NQ> h4 = bytes_to_half<STRIP>(raw_nn);
     RawRow<STRIP> pv; pv.load(prev + (j + 2) * kCombTW);
     const int f = j & 1;          // accumulator slot; mapped to the field parity after the loop
-    // rows y < 2 and y >= H-2 have no comb response (spec): an infinite threshold switches them off
+    // rows y < 2 and y >= H-2 have no comb response (spec): edge tiles read per-row thresholds (infinite there)
+    // from a small shared table built once per segment -- two LDS instead of compare/select on the ALU pipe
     __half2 tS = thS, tL = thL;
     if (EDGE) {
-      const int y = y_first + j;
-      if (y < 2 || y >= H - 2) { const uint32_t inf2 = 0x7C007C00u; tS = *reinterpret_cast<const __half2*>(&inf2); tL = tS; }
+      tS = *reinterpret_cast<const __half2*>(&th_rows[j]);
+      tL = *reinterpret_cast<const __half2*>(&th_rows[Cfg::R + j]);
     }
 #pragma unroll
     for (int q = 0; q < NQ; q += 2) {
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
   uint8_t* tiles = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ unsigned int red[2][3];
+  __shared__ uint32_t th_tab[Cfg::RUNS][2][Cfg::R];          // EDGE tiles: per-row thresholds of every run
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -223,6 +225,15 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
       const int pro = nloads < S ? nloads : S;
       for (int j = 0; j < pro; ++j) issue(j);
     }
+    if (edge) {                                      // (re)build the per-row threshold table of this tile
+      for (int i = tid; i < Cfg::RUNS * Cfg::R; i += Cfg::THREADS) {
+        const int y = y0 + i;
+        const bool ok = y >= 2 && y < P.H - 2;
+        th_tab[i / Cfg::R][0][i % Cfg::R] = ok ? P.thS : 0x7C007C00u;
+        th_tab[i / Cfg::R][1][i % Cfg::R] = ok ? P.thL : 0x7C007C00u;
+      }
+      __syncthreads();
+    }
     mbar_wait(&full_bar[gload % S], (gload / S) & 1u);      // L_0
     for (int k = 1; k <= nf; ++k) {
       const uint32_t g = gload + (uint32_t)k;
@@ -232,9 +243,9 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
       const uint8_t* prv = tiles + stp * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
       uint32_t vS = 0, vL = 0, vM = 0;
       if (!edge) {
-        comb_tile_rows<Cfg, false>(cur, prv, y_first, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
+        comb_tile_rows<Cfg, false>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
       } else if (rows_live) {
-        comb_tile_rows<Cfg, true>(cur, prv, y_first, P.H, P.thM, P.thS, P.thL, vS, vL, vM);
+        comb_tile_rows<Cfg, true>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
       }
       vS = __reduce_add_sync(0xFFFFFFFFu, vS);
       vL = __reduce_add_sync(0xFFFFFFFFu, vL);
@@ -252,6 +263,55 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
       ++gstep;
     }
     gload += (uint32_t)nloads;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Generic fallback: any sample size (8/10/12/16-bit) and any pitch.  One thread per pixel, plain cached loads,
+// ballot/popc counting.  Used for YUV420P10..16 clips and for 8-bit layouts TMA cannot describe (pitch or offsets
+// not multiples of 16 bytes).  Same integer spec, same results; roughly an order of magnitude below the streaming
+// kernel (it re-reads the previous frame and the vertical neighbours through L1/L2).
+// ---------------------------------------------------------------------------------------------------------
+struct CombGenericArgs {
+  const uint8_t* base; long long frame_stride; long long off[3];
+  int pitch[3];            // ELEMENTS
+  int W[3], H[3];
+  int thM[3], thS[3], thL[3];
+  int first_frame;         // window-relative index of the first frame to analyse
+  int prev_of_first;       // window-relative index of its predecessor (== first_frame when there is none)
+  int nframes;
+  int* counts;             // row 0 = first_frame
+};
+
+template <typename pixel_t>
+__global__ void __launch_bounds__(256) comb_generic_kernel(const CombGenericArgs a) {
+  const int pl = blockIdx.z % 3, f = blockIdx.z / 3;
+  const int W = a.W[pl], H = a.H[pl], pitch = a.pitch[pl];
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);          // one warp = one row segment => uniform field parity
+  if (blockIdx.x * 32 >= W || blockIdx.y * 8 >= H) return;
+  const int cur_f = a.first_frame + f, prev_f = f == 0 ? a.prev_of_first : cur_f - 1;
+  const pixel_t* cur = reinterpret_cast<const pixel_t*>(a.base + (long long)cur_f * a.frame_stride + a.off[pl]);
+  const pixel_t* prv = reinterpret_cast<const pixel_t*>(a.base + (long long)prev_f * a.frame_stride + a.off[pl]);
+  bool mv = false, sh = false, lsh = false;
+  if (x < W && y < H) {
+    const long long o = x + (long long)y * pitch;
+    const int c = cur[o];
+    int d = c - (int)prv[o]; d = d < 0 ? -d : d;
+    mv = d >= a.thM[pl];
+    if (y >= 2 && y < H - 2) {
+      int v = (int)cur[o - 2 * (long long)pitch] + 4 * c + (int)cur[o + 2 * (long long)pitch]
+              - 3 * ((int)cur[o - pitch] + (int)cur[o + pitch]);
+      v = v < 0 ? -v : v;
+      sh = v >= a.thS[pl]; lsh = v >= a.thL[pl];
+    }
+  }
+  const unsigned bm = __ballot_sync(0xFFFFFFFFu, mv), bs = __ballot_sync(0xFFFFFFFFu, sh), bl = __ballot_sync(0xFFFFFFFFu, lsh);
+  if ((threadIdx.x & 31) == 0 && y < H) {
+    int* o = a.counts + (size_t)f * 12 + (pl ? 6 : 0) + (y & 1) * 3;
+    if (bm) atomicAdd(o + 0, __popc(bm));
+    if (bs) atomicAdd(o + 1, __popc(bs));
+    if (bl) atomicAdd(o + 2, __popc(bl));
   }
 }
 

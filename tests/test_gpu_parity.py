@@ -291,5 +291,27 @@ def test_scan_frames_unaligned_pitch_fallback(ctx, oracle):
     Y, _, _ = synth.split_planes(fr, w, h)
     ref = np.stack([o.scan_frame(Y[i]) for i in range(n)])
     assert np.array_equal(_bits(out[:, 0]), _bits(ref))
-    with pytest.raises(ab.AmtkError, match="multiples of 16"):
-        ctx.comb_frames(_clip(fr, w, h))
+    # the combing metric takes the generic (non-TMA) kernel for this layout: same counters
+    got = ctx.comb_frames(_clip(fr, w, h)).cpu().numpy()
+    _, U, V = synth.split_planes(fr, w, h)
+    assert np.array_equal(got, po.or_comb_clip(Y, U, V, ab.default_comb_params().as_list()))
+
+
+def test_comb_16bit_generic_kernel(ctx, oracle):
+    """YUV420P10 clips: the integer spec on u16 samples (generic kernel), incl. range calls with a halo frame."""
+    po = oracle
+    w, h, n = 224, 136, 7
+    f8 = synth.make_frames(2, n, w, h, device="cuda", mode="telecine")
+    f16 = (f8.to(torch.int32) * 4 + (f8.to(torch.int32) & 3)).to(torch.int16).contiguous()
+    clip = ab.yv12_clip(f16, w, h, n, True, bits=10)
+    prm = ab.default_comb_params()
+    prm.th_move_y, prm.th_shima_y, prm.th_lshima_y = 80, 48, 3000
+    prm.th_move_c, prm.th_shima_c, prm.th_lshima_c = 200, 64, 144
+    got = ctx.comb_frames(clip, prm).cpu().numpy()
+    a16 = f16.cpu().numpy().view(np.uint16)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    Y = a16[:, :ysz].reshape(n, h, w); U = a16[:, ysz:ysz + csz].reshape(n, h // 2, w // 2); V = a16[:, ysz + csz:].reshape(n, h // 2, w // 2)
+    ref = po.or_comb_clip(Y, U, V, prm.as_list())
+    assert np.array_equal(got, ref) and ref[:, 1].sum() > 0
+    part = np.concatenate([ctx.comb_frames(clip, prm, 0, 3).cpu().numpy(), ctx.comb_frames(clip, prm, 3, 4).cpu().numpy()])
+    assert np.array_equal(part, ref)

@@ -19,15 +19,16 @@ for n0 in range(0, frames, 20):
 clip = ab.yv12_clip(clip_t, W, H, frames, True)
 prm = ab.default_comb_params()
 ref = None
-combos = [(8, 3, 0, 0, 128), (8, 2, 0, 0, 128), (8, 2, 5, 0, 128), (8, 2, 0, 0, 0), (4, 2, 0, 0, 128), (4, 3, 0, 0, 128)]
+combos = [(8, 3, 0, 0, 128, 0), (8, 2, 0, 0, 128, 0), (8, 4, 0, 0, 128, 0), (8, 2, 4, 0, 128, 0)]
 if len(sys.argv) > 1:
     combos = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
-for strip, stages, ctas, acc, l2 in combos:
+for strip, stages, ctas, acc, l2, R in combos:
     os.environ["AMTK_COMB_STRIP"] = str(strip)
     os.environ["AMTK_COMB_STAGES"] = str(stages)
     os.environ["AMTK_COMB_CTAS"] = str(ctas)
     os.environ["AMTK_COMB_ACC"] = str(acc)
     os.environ["AMTK_COMB_L2"] = str(l2)
+    os.environ["AMTK_COMB_R"] = str(R)
     ctx = ab.Context(0, torch.cuda.current_stream().cuda_stream)
     out = ctx.comb_frames(clip, prm)
     torch.cuda.synchronize()
@@ -39,5 +40,5 @@ for strip, stages, ctas, acc, l2 in combos:
     if ref is None:
         ref = o
     gbs = frames * W * H * 1.5 / (ms / n * 1e-3) / 1e9
-    print("strip=%d stages=%d ctas=%d acc=%d l2=%d: %.3f ms/launch  %.0f GB/s  %.0f fps  same=%s" % (strip, stages, ctas, acc, l2, ms / n, gbs, frames / (ms / n * 1e-3), np.array_equal(o, ref)), flush=True)
+    print("strip=%d stages=%d ctas=%d acc=%d l2=%d R=%d: %.3f ms/launch  %.0f GB/s  %.0f fps  same=%s" % (strip, stages, ctas, acc, l2, R, ms / n, gbs, frames / (ms / n * 1e-3), np.array_equal(o, ref)), flush=True)
     ctx.close()
