@@ -81,6 +81,7 @@ SIGNATURES = [
     ("amtk_scan_num_valid", C.c_int, [V]),
     ("amtk_scan_get_sums", C.c_int, [V, C.POINTER(C.c_double)]),
     ("amtk_scan_get_logo", C.c_int, [V, C.c_int, C.c_int, c_float_p]),
+    ("amtk_scan_logo", C.c_int, [V, C.POINTER(ClipDesc), C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, V]),
     ("amtk_erase_logo_frames", C.c_int, [V, C.POINTER(ClipDesc), V, C.c_int, C.c_int, c_float_p]),
     ("amtk_calc_fade2", None, [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]),
 ]
@@ -242,6 +243,13 @@ class Context:
         n = clip.num_frames - frame0 if nframes is None else nframes
         f = np.ascontiguousarray(fades, np.float32).reshape(n, 2)
         check(self.L.amtk_erase_logo_frames(self.h, C.byref(clip), logo.h, frame0, n, f.ctypes.data_as(c_float_p)))
+
+    def scan_logo(self, clip, dstpath, imgx, imgy, w, h, thy, max_frames, service_id=0, cb=None):
+        """The reference's ScanLogo pipeline (LogoScan.hpp:1058-1098) on a clip; cb(progress, nread, total, ngather)."""
+        CB = C.CFUNCTYPE(C.c_int, C.c_float, C.c_int, C.c_int, C.c_int)
+        fn = CB(lambda p, a, b, c: int(bool(cb(p, a, b, c)))) if cb else None
+        check(self.L.amtk_scan_logo(self.h, C.byref(clip), service_id, dstpath.encode(), imgx, imgy, w, h, thy, max_frames,
+                                    C.cast(fn, C.c_void_p) if fn else None))
 
     def logo_scan(self, scanw, scanh, thy, log_uvx=1, log_uvy=1):
         out = C.c_void_p()

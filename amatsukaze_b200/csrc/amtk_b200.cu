@@ -6,6 +6,8 @@
 #include "comb_kernels.cuh"
 #include "scan_kernels.cuh"
 #include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -884,6 +886,66 @@ int amtk_scan_get_logo(amtk_scan* s, int maxv, int clean, float* data) {
   if (!amtk::scan_finalize(sums.data(), s->nvalid, s->scanw, s->scanh, s->logUVx, s->logUVy, maxv, clean != 0, data))
     AMTK_FAIL("Insufficient logo frames");
   return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ScanLogo pipeline (LogoScan.hpp:794-1098)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct ScanGuard { amtk_scan* s = nullptr; ~ScanGuard() { if (s) amtk_scan_destroy(s); } };
+struct LogoGuard { amtk_logo* l = nullptr; ~LogoGuard() { if (l) amtk_logo_destroy(l); } };
+}
+
+int amtk_scan_logo(amtk_ctx* ctx, const amtk_clip* clip, int service_id, const char* dstpath,
+                   int imgx, int imgy, int w, int h, int thy, int max_frames, amtk_logo_analyze_cb cb) {
+  if (!ctx || !dstpath) AMTK_FAIL("amtk_scan_logo: null argument");
+  if (!validate_clip(clip, true)) return 0;
+  if (clip->bytes_per_sample != 1) AMTK_FAIL("LogoScan supports 8-bit clips only (as the reference, LogoScan.hpp:812)");
+  const int n = clip->num_frames;
+  // ---- MakeInitialLogo (:917-921): every frame is offered until max_frames valid ones were gathered ----
+  std::vector<uint8_t> valid((size_t)n), select((size_t)n, 0);
+  {
+    ScanGuard probe;                       // pass 1: validity of every frame
+    if (!amtk_scan_create(ctx, w, h, clip->log_uvx, clip->log_uvy, thy, &probe.s)) return 0;
+    if (!amtk_scan_add_frames(probe.s, clip, imgx, imgy, 0, n, nullptr, valid.data())) return 0;
+  }
+  int numFrames = 0, nread = 0;
+  for (int i = 0; i < n && numFrames < max_frames; ++i) { ++nread; if (valid[i]) { select[i] = 1; ++numFrames; } }
+  if (cb && !cb(50.0f * nread / std::max(1, n), nread, 0, numFrames)) AMTK_FAIL("Cancel requested");
+  const size_t ndata = ((size_t)w * h + 2 * (size_t)(w >> clip->log_uvx) * (h >> clip->log_uvy)) * 2;
+  std::vector<float> logodata(ndata);
+  {
+    ScanGuard init;
+    if (!amtk_scan_create(ctx, w, h, clip->log_uvx, clip->log_uvy, thy, &init.s)) return 0;
+    if (!amtk_scan_add_frames(init.s, clip, imgx, imgy, 0, n, select.data(), nullptr)) return 0;
+    if (!amtk_scan_get_logo(init.s, 255, 0, logodata.data())) return 0;      // "Insufficient logo frames"
+  }
+  // ---- ReMakeLogo x2 (:923-1036) ----
+  float fades[20];
+  for (int fi = 0; fi < 20; ++fi) fades[fi] = 0.1f * fi;                      // :967
+  std::vector<float> sweep((size_t)n * 20);
+  for (int round = 0; round < 2; ++round) {
+    LogoGuard raw, deint;
+    if (!amtk_logo_create(ctx, logodata.data(), w, h, clip->log_uvx, clip->log_uvy, w, h, imgx, imgy, &raw.l)) return 0;
+    if (!amtk_logo_deint(raw.l, &deint.l) || !amtk_logo_create_mask(deint.l, 0.1f)) return 0;      // :929-931
+    if (!amtk_logo_eval_fades(ctx, clip, deint.l, fades, 20, 0, n, sweep.data(), 0)) return 0;
+    std::vector<uint8_t> sel2((size_t)n, 0);
+    for (int i = 0; i < n; ++i) {
+      if (!select[i]) continue;
+      float best = FLT_MAX; int bi = 0;                                        // :964-975, first strict minimum of |score|
+      for (int fi = 0; fi < 20; ++fi) { const float r = std::fabs(sweep[(size_t)i * 20 + fi]); if (r < best) { best = r; bi = fi; } }
+      sel2[i] = bi > 8;                                                         // :1018-1021
+    }
+    if (cb && !cb(50.0f + 25.0f * (round + 1) - 0.01f, n, numFrames, numFrames)) AMTK_FAIL("Cancel requested");
+    ScanGuard acc;
+    if (!amtk_scan_create(ctx, w, h, clip->log_uvx, clip->log_uvy, thy, &acc.s)) return 0;
+    if (!amtk_scan_add_frames(acc.s, clip, imgx, imgy, 0, n, sel2.data(), nullptr)) return 0;
+    if (!amtk_scan_get_logo(acc.s, 255, 1, logodata.data())) return 0;        // :1030-1035
+  }
+  if (cb && !cb(1.0f, numFrames, numFrames, numFrames)) AMTK_FAIL("Cancel requested");     // :1071-1073
+  LogoGuard fin;                                                                // :1075-1078
+  if (!amtk_logo_create(nullptr, logodata.data(), w, h, clip->log_uvx, clip->log_uvy, clip->width, clip->height, imgx, imgy, &fin.l)) return 0;
+  return amtk_logo_save(fin.l, dstpath, "No Name", service_id);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -174,6 +174,17 @@ AMTK_API int amtk_scan_get_sums(amtk_scan* s, double* out);
  * "Insufficient logo frames" when the reference would return nullptr (:847-849). */
 AMTK_API int amtk_scan_get_logo(amtk_scan* s, int maxv, int clean, float* data);
 
+/* The whole logo-generation pipeline of the reference's ScanLogo C export (LogoScan.hpp:1083-1098 ->
+ * LogoAnalyzer::ScanLogo :1058-1079): MakeInitialLogo (:917-921, AddFrame on every frame until max_frames valid ones),
+ * ReMakeLogo twice (:923-1036: deint logo, mask 0.1, 20-fade sweep per valid frame, re-accumulate frames whose best
+ * fade index is > 8, GetLogo(clean)), then LogoData::Save.  The clip stands where the reference decodes `srcpath`;
+ * the valid ROI frames stay in HBM instead of the UtVideo work file.  cb (may be NULL) has the reference's
+ * LOGO_ANALYZE_CB signature (:792): bool(float progress, int nread, int total, int ngather); returning 0 cancels
+ * ("Cancel requested", :908-910).  Only 8-bit clips, like the reference (:812). */
+typedef int (*amtk_logo_analyze_cb)(float progress, int nread, int total, int ngather);
+AMTK_API int amtk_scan_logo(amtk_ctx* ctx, const amtk_clip* clip, int service_id, const char* dstpath,
+                            int imgx, int imgy, int w, int h, int thy, int max_frames, amtk_logo_analyze_cb cb);
+
 /* ---------------------------------------------------------------------------------------------
  * Logo erase (replaces AMTEraseLogo::Delogo on Y,U,V, LogoScan.hpp:1248-1261,1374-1397), in place on a
  * device-resident or host clip.  fades float[nframes][2] = fadeT,fadeB per frame (host pointer).

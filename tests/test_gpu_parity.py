@@ -315,3 +315,54 @@ def test_comb_16bit_generic_kernel(ctx, oracle):
     assert np.array_equal(got, ref) and ref[:, 1].sum() > 0
     part = np.concatenate([ctx.comb_frames(clip, prm, 0, 3).cpu().numpy(), ctx.comb_frames(clip, prm, 3, 4).cpu().numpy()])
     assert np.array_equal(part, ref)
+
+
+def test_scan_logo_pipeline(ctx, oracle, tmp_path):
+    """amtk_scan_logo = the reference's ScanLogo pipeline (LogoScan.hpp:1058-1098): MakeInitialLogo, ReMakeLogo x2,
+    Save -- compared with the same pipeline composed from the oracle's pieces."""
+    po = oracle
+    w, h, sx, sy, sw, sh, n, thy, maxf = 320, 192, 200, 64, 64, 48, 90, 12, 40
+    lg = synth.make_logo(sw, sh, seed=4)
+    fr = synth.make_frames(0, n, w, h, seed=0x5EED0004, device="cuda", mode="flat", logo=lg, imgx=sx, imgy=sy)
+    clip = _clip(fr, w, h)
+    dst = str(tmp_path / "gen.lgd")
+    calls = []
+    ctx.scan_logo(clip, dst, sx, sy, sw, sh, thy, maxf, service_id=410, cb=lambda p, a, b, c: calls.append((p, a, b, c)) or True)
+    assert calls and calls[-1][0] == 1.0
+    got = ab.Logo.load(dst)
+    gi = got.info()
+    assert (gi.w, gi.h, gi.imgw, gi.imgh, gi.imgx, gi.imgy) == (sw, sh, w, h, sx, sy)
+    # ---- oracle composition ----
+    Y, U, V = synth.split_planes(fr, w, h)
+    roi = lambda i: (Y[i][sy:sy + sh, sx:sx + sw], U[i][sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2], V[i][sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2])
+    sc = po.OracleScan(sw, sh, thy)
+    stored = []
+    for i in range(n):
+        if len(stored) >= maxf:
+            break
+        if sc.add_frame(*roi(i)):
+            stored.append(i)
+    assert len(stored) == maxf and stored[-1] < n - 10        # the cut-off really bites
+    data = sc.get_logo(255, False)
+    for _ in range(2):
+        de = po.OracleLogo.create(data, sw, sh, sw, sh, 0, 0).deint().create_mask(0.1)
+        keep = []
+        for i in stored:
+            ry = np.ascontiguousarray(roi(i)[0])
+            dd = np.zeros(sw * sh + 8, np.float32)
+            po.oracle_lib().amtk_or_deint_y_u8(dd.ctypes.data_as(po.c_float_p), ry.ctypes.data_as(po.c_u8_p), sw, sw, sh)
+            res = [abs(np.float32(de.evaluate(dd, 255.0, np.float32(0.1) * np.float32(fi)))) for fi in range(20)]
+            if int(np.argmin(res)) > 8:
+                keep.append(i)
+        assert 0 < len(keep) < len(stored)
+        sc2 = po.OracleScan(sw, sh, thy)
+        for i in keep:
+            sc2.add_frame(*roi(i))
+        data = sc2.get_logo(255, True)
+        assert data is not None
+    assert np.array_equal(got.tables()["data"].view(np.uint32), data.view(np.uint32))
+    # cancel + insufficient frames behave like the reference
+    with pytest.raises(ab.AmtkError, match="Cancel requested"):
+        ctx.scan_logo(clip, dst, sx, sy, sw, sh, thy, maxf, cb=lambda *a: False)
+    with pytest.raises(ab.AmtkError, match="Insufficient logo frames"):
+        ctx.scan_logo(clip, dst, sx, sy, sw, sh, 0, maxf)
