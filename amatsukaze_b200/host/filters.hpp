@@ -540,11 +540,127 @@ inline void ReadAllFrames(PClip clip, IScriptEnvironment* env) {
   for (int i = 0; i < n; ++i) clip->GetFrame(i, env);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Telecine side files and their consumers
+// ---------------------------------------------------------------------------------------------------------------
+// AMTDecimate (FilteredSource.hpp:637-676): <tmp>.duration.txt holds one integer per OUTPUT frame = how many source
+// frames it lasts; output frame i shows source frame sum(durations[0..i)).
+class AMTDecimate : public GenericVideoFilter {
+  std::vector<int> durations, framesMap;
+public:
+  AMTDecimate(PClip source, const std::string& duration, IScriptEnvironment* env) : GenericVideoFilter(source) {
+    FILE* fp = fopen(duration.c_str(), "r");
+    if (!fp) env->ThrowError("[AMTDecimate] failed to open %s", duration.c_str());
+    char line[256];
+    while (fgets(line, sizeof(line), fp)) durations.push_back(std::atoi(line));
+    fclose(fp);
+    const int numSourceFrames = std::accumulate(durations.begin(), durations.end(), 0);
+    if (vi.num_frames != numSourceFrames)
+      env->ThrowError("[AMTDecimate] # of frames does not match. %d(%s) vs %d(source clip)", numSourceFrames, duration.c_str(), vi.num_frames);
+    vi.num_frames = (int)durations.size();
+    framesMap.assign(durations.size(), 0);
+    for (size_t i = 0; i + 1 < durations.size(); ++i) framesMap[i + 1] = framesMap[i] + durations[i];
+  }
+  PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment* env) override {
+    return child->GetFrame(framesMap[std::max(0, std::min(n, vi.num_frames - 1))], env);
+  }
+  int SourceFrame(int n) const { return framesMap[std::max(0, std::min(n, (int)framesMap.size() - 1))]; }
+  static AVSValue __cdecl Create(AVSValue args, void*, IScriptEnvironment* env) {
+    return AVSValue(PClip(new AMTDecimate(args[0].AsClip(), args[1].AsString(), env)));
+  }
+};
+
+// AMTFilterSource::readTimecodeFile + readTimecode (FilteredSource.hpp:163-212): timestamps in ms, one per line,
+// '#' comments, optional "# total: <seconds>"; the end time is extrapolated when absent; the VFR base rate is the one
+// of 60/120/240 (x1000/1001) whose grid fits the timestamps best.
+struct TimecodeFile {
+  std::vector<double> timeCodes;
+  int vfrTimingFps = 0;
+  bool read(const std::string& path) {
+    FILE* fp = fopen(path.c_str(), "r");
+    if (!fp) return false;
+    std::regex re("#\\s*total:\\s*([+-]?([0-9]*[.])?[0-9]+).*");
+    char line[512];
+    timeCodes.clear();
+    bool total = false;
+    while (!total && fgets(line, sizeof(line), fp)) {
+      std::string str(line);
+      while (!str.empty() && (str.back() == '\n' || str.back() == '\r')) str.pop_back();
+      if (str.empty()) continue;
+      std::smatch m;
+      if (std::regex_search(str, m, re)) { timeCodes.push_back(std::atof(m[1].str().c_str()) * 1000); total = true; }
+      else if (str[0] != '#') timeCodes.push_back(std::atoi(str.c_str()));
+    }
+    fclose(fp);
+    if (!total) {
+      const size_t n = timeCodes.size();
+      if (n >= 2) timeCodes.push_back(timeCodes[n - 1] * 2 - timeCodes[n - 2]);
+      else if (n == 1) timeCodes.push_back(timeCodes[0] + 1000.0 / 60.0);
+    }
+    if (timeCodes.empty()) return true;
+    double minDiff = timeCodes.back();
+    const double epsilon = timeCodes.size() * 10e-10;
+    for (int fps : { 60, 120, 240 }) {
+      const double mult = fps / 1001.0, inv = 1.0 / mult;
+      double diff = 0;
+      for (double ts : timeCodes) diff += std::abs(inv * std::round(ts * mult) - ts);
+      if (diff < minDiff - epsilon) { vfrTimingFps = fps; minDiff = diff; }
+    }
+    return true;
+  }
+};
+
+// Pulldown classification from the combing counters (this repo's heuristic; the reference delegates the decision to
+// the external KFM plugin).  3:2 telecine shows up as two adjacent combed frames in every 5-frame cycle.  The cycle
+// phase is taken from the whole clip (the frame pair position with the largest summed comb response); a cycle whose
+// pair stands out by `ratio` against its other three frames becomes 4 film frames (durations 1,1,2,1: the film frame
+// that straddles the combed pair lasts two video frames), any other cycle passes through as 5 x 1.
+// Writes <base>.duration.txt (AMTDecimate) and <base>.timecode.txt (ms per output frame, "# total:" trailer).
+// Returns the number of film cycles, -1 on I/O error.
+inline int WriteTelecineFiles(const std::vector<int32_t>& counts, int num_frames, unsigned fps_num, unsigned fps_den,
+                              const std::string& base, double ratio = 2.0) {
+  // the large-threshold response ("lshima", Y top+bottom) separates real combing from vertical detail best
+  auto shima = [&](int n) { return (long long)counts[(size_t)n * 12 + 2] + counts[(size_t)n * 12 + 5]; };
+  int phase = 0; long long best = -1;
+  for (int p = 0; p < 5; ++p) {
+    long long acc = 0;
+    for (int n = p; n + 1 < num_frames; n += 5) acc += std::min(shima(n), shima(n + 1));
+    if (acc > best) { best = acc; phase = p; }
+  }
+  const int start = (phase + 3) % 5;                      // cycles begin two frames before the combed pair
+  std::vector<int> durations;
+  int film_cycles = 0, n = 0;
+  for (; n < start && n < num_frames; ++n) durations.push_back(1);
+  for (; n + 5 <= num_frames; n += 5) {
+    const long long pair = std::min(shima(n + 2), shima(n + 3));
+    const long long rest = std::max(std::max(shima(n), shima(n + 1)), shima(n + 4));
+    if ((double)pair > ratio * (double)std::max<long long>(rest, 1)) {
+      ++film_cycles;
+      const int d[4] = { 1, 1, 2, 1 };
+      durations.insert(durations.end(), d, d + 4);
+    } else {
+      durations.insert(durations.end(), 5, 1);
+    }
+  }
+  for (; n < num_frames; ++n) durations.push_back(1);
+  FILE* fd = fopen((base + ".duration.txt").c_str(), "w");
+  FILE* ft = fopen((base + ".timecode.txt").c_str(), "w");
+  if (!fd || !ft) { if (fd) fclose(fd); if (ft) fclose(ft); return -1; }
+  fprintf(ft, "# timecode format v2\n");
+  const double frame_ms = 1000.0 * fps_den / fps_num;
+  int src = 0;
+  for (int d : durations) { fprintf(fd, "%d\n", d); fprintf(ft, "%d\n", (int)std::round(src * frame_ms)); src += d; }
+  fprintf(ft, "# total: %.6f\n", src * frame_ms / 1000.0);
+  fclose(fd); fclose(ft);
+  return film_cycles;
+}
+
 // Registration with the reference's names and argument specs (Amatsukaze.cpp:43-66).
 extern "C" inline const char* __stdcall AvisynthPluginInit3(IScriptEnvironment* env, const AVS_Linkage* const) {
   env->AddFunction("AMTSource", "s[filter]s[outqp]b", av::CreateAMTSource, 0);
   env->AddFunction("AMTAnalyzeLogo", "cs[maskratio]i", logo::AMTAnalyzeLogo::Create, 0);
   env->AddFunction("AMTEraseLogo", "ccs[logof]s[mode]i[maxfade]i", logo::AMTEraseLogo::Create, 0);
+  env->AddFunction("AMTDecimate", "c[duration]s", AMTDecimate::Create, 0);
   env->AddFunction("AMTCombAnalyze", "c[filepath]s", AMTCombAnalyze::Create, 0);
   return "Amatsukaze plugin (B200 hot path)";
 }

@@ -82,7 +82,7 @@ def _plane(n, H, W, plane, seed, mode, speed):
     dev = n.device
     y = torch.arange(H, device=dev, dtype=torch.int64).view(1, H, 1)
     x = torch.arange(W, device=dev, dtype=torch.int64).view(1, 1, W)
-    noise = (_hash32(x, y, n, plane, seed) & 7) - 3
+    noise = (_hash32(x, y, n, plane, seed) & 3) - 1          # -1..2: below the default combing thresholds
     if mode == "flat":
         g = 40 + (_hash32(n, n * 0 + 7, n * 0, 3, seed) % 160) if plane == 0 else 128 + ((_hash32(n, n * 0 + 9, n * 0, plane, seed) & 15) - 8)
         bad = (_hash32(n, n * 0 + 11, n * 0, 5, seed) % 10) < 3          # ~30 % of frames get a gradient -> fail thy
@@ -93,20 +93,21 @@ def _plane(n, H, W, plane, seed, mode, speed):
     par = y & 1
     t = _field_time(n, par, mode)                                        # (N,H,1)
     if plane == 0:
-        v = 64 + ((3 * x + 5 * y) & 63)
+        tri = (3 * x + 5 * y) & 127                      # triangular ramp: continuous, so only real motion combs
+        v = 64 + torch.where(tri < 64, tri, 127 - tri)
         bx = (speed * 4 * t) % (W + 128) - 128
         inbar = (x >= bx) & (x < bx + 128)
         v = torch.where(inbar, 180 + ((x - bx) & 15), v)
         ty0, ty1, tx0, tx1 = H // 3, (2 * H) // 3, W // 4, (3 * W) // 4
         intex = (y >= ty0) & (y < ty1) & (x >= tx0) & (x < tx1)
-        tex = 48 + (_hash32(x - speed * t, y >> 1, n * 0, 9, seed) & 127)
+        tex = 48 + (_hash32((x - speed * t) >> 2, y >> 3, n * 0, 9, seed) & 127)     # 4x8-pixel blocks moving horizontally
         v = torch.where(intex, tex, v)
         v = v + noise
         return torch.clamp(v, 16, 235)
     v = 128 + noise
     ty0, ty1, tx0, tx1 = H // 3, (2 * H) // 3, W // 4, (3 * W) // 4
     intex = (y >= ty0) & (y < ty1) & (x >= tx0) & (x < tx1)
-    tex = 112 + (_hash32(x - (speed * t) // 2, y >> 1, n * 0, 9 + plane, seed) & 31)
+    tex = 112 + (_hash32((x - (speed * t) // 2) >> 2, y >> 2, n * 0, 9 + plane, seed) & 31)
     v = torch.where(intex, tex + noise, v)
     return torch.clamp(v, 16, 240)
 

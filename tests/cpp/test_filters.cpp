@@ -65,6 +65,25 @@ int main(int argc, char** argv) {
     // ---- telecine pre-pass: every frame pulled and discarded (FilteredSource.hpp:417-439) ----
     PClip pre = env->Invoke("AMTCombAnalyze", AVSValue(std::vector<AVSValue>{ AVSValue(clip), AVSValue(out + "/combstat.txt") })).AsClip();
     ReadAllFrames(pre, env);
+    // ---- side files of the telecine pass and their consumers (FilteredSource.hpp:163-212,265-271,637-676) ----
+    {
+      AMTCombAnalyze* ca = dynamic_cast<AMTCombAnalyze*>(pre.get());
+      const int film = WriteTelecineFiles(ca->Counts(env), vi.num_frames, vi.fps_numerator, vi.fps_denominator, out + "/tc");
+      PClip dec = env->Invoke("AMTDecimate", AVSValue(std::vector<AVSValue>{ AVSValue(clip), AVSValue(out + "/tc.duration.txt") })).AsClip();
+      TimecodeFile tc;
+      const bool ok = tc.read(out + "/tc.timecode.txt");
+      printf("telecine: film_cycles=%d decimated=%d timecodes=%zu total_ms=%.3f vfrfps=%d ok=%d\n", film,
+             dec->GetVideoInfo().num_frames, tc.timeCodes.size(), tc.timeCodes.empty() ? 0.0 : tc.timeCodes.back(), tc.vfrTimingFps, (int)ok);
+      AMTDecimate* d = dynamic_cast<AMTDecimate*>(dec.get());
+      printf("decimate map:");
+      for (int i = 0; i < std::min(10, dec->GetVideoInfo().num_frames); ++i) printf(" %d", d->SourceFrame(i));
+      printf("\n");
+      try {
+        FILE* fp = fopen((out + "/bad.duration.txt").c_str(), "w"); fprintf(fp, "1\n2\n"); fclose(fp);
+        env->Invoke("AMTDecimate", AVSValue(std::vector<AVSValue>{ AVSValue(clip), AVSValue(out + "/bad.duration.txt") }));
+        rc = 1;
+      } catch (const AvisynthError& e) { printf("expected error: %s\n", e.msg.c_str()); }
+    }
     // ---- error behaviour ----
     try {
       env->Invoke("AMTAnalyzeLogo", AVSValue(std::vector<AVSValue>{ AVSValue(clip), AVSValue(out + "/nope.lgd"), AVSValue(35) }));

@@ -124,6 +124,32 @@ def test_erase_through_getframe(run):
     assert changed > 0
 
 
+def test_telecine_side_files(tmp_path_factory):
+    """A 3:2 pulled-down clip through AMTCombAnalyze -> WriteTelecineFiles -> AMTDecimate / timecode reader."""
+    exe = _build.HOST_TEST
+    out = tmp_path_factory.mktemp("telecine")
+    n = 43
+    frames = synth.make_frames(0, n, W, H, mode="telecine").numpy()
+    clip = out / "clip.amtsraw"
+    with open(clip, "wb") as f:
+        f.write(b"AMTSRAW1" + struct.pack("<6i", W, H, 8, n, 30000, 1001))
+        f.write(frames.tobytes())
+    lg = synth.make_logo(64, 64, seed=1)
+    logo_path = str(out / "logo.lgd")
+    ab.Logo.create(lg["data"], 64, 64, W, H, IMGX, IMGY).save(logo_path)
+    r = subprocess.run([exe, str(clip), logo_path, str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("telecine:")][0]
+    kv = dict(p.split("=") for p in line.split()[1:])
+    assert int(kv["film_cycles"]) == 8                       # 43 frames = 8 full cycles + 3
+    assert int(kv["decimated"]) == n - 8
+    dur = [int(x) for x in open(out / "tc.duration.txt").read().split()]
+    assert sum(dur) == n and dur[:5] == [1, 1, 2, 1, 1]      # synthetic pattern: frames 2,3 of every cycle are combed
+    assert "decimate map: 0 1 2 4 5 6 7 9 10 11" in r.stdout
+    assert int(kv["timecodes"]) == n - 8 + 1 and abs(float(kv["total_ms"]) - n * 1001 / 30) < 1e-3
+    assert "[AMTDecimate] # of frames does not match. 3(" in r.stdout      # FilteredSource.hpp:653-654
+
+
 def test_comb_prepass_file(run):
     out, frames = run["out"], run["frames"]
     got = np.loadtxt(out / "combstat.txt", dtype=np.int64).astype(np.int32)
