@@ -82,6 +82,7 @@ SIGNATURES = [
     ("amtk_scan_get_sums", C.c_int, [V, C.POINTER(C.c_double)]),
     ("amtk_scan_get_logo", C.c_int, [V, C.c_int, C.c_int, c_float_p]),
     ("amtk_scan_logo", C.c_int, [V, C.POINTER(ClipDesc), C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, V]),
+    ("amtk_weave_frames", C.c_int, [V, C.POINTER(ClipDesc), C.POINTER(ClipDesc), C.c_int, c_i32_p, c_i32_p, C.c_int, C.c_int]),
     ("amtk_erase_logo_frames", C.c_int, [V, C.POINTER(ClipDesc), V, C.c_int, C.c_int, c_float_p]),
     ("amtk_calc_fade2", None, [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]),
 ]
@@ -250,6 +251,14 @@ class Context:
         fn = CB(lambda p, a, b, c: int(bool(cb(p, a, b, c)))) if cb else None
         check(self.L.amtk_scan_logo(self.h, C.byref(clip), service_id, dstpath.encode(), imgx, imgy, w, h, thy, max_frames,
                                     C.cast(fn, C.c_void_p) if fn else None))
+
+    def weave_frames(self, src, dst, top_idx, bottom_idx, dst_frame0=0, src_is_nv12=False):
+        """AMTSource::MergeField on the device: dst[k] even rows <- src[top_idx[k]], odd rows <- src[bottom_idx[k]]."""
+        t = np.ascontiguousarray(top_idx, np.int32)
+        b = np.ascontiguousarray(bottom_idx, np.int32)
+        assert t.shape == b.shape
+        check(self.L.amtk_weave_frames(self.h, C.byref(src), C.byref(dst), dst_frame0, t.ctypes.data_as(c_i32_p),
+                                       b.ctypes.data_as(c_i32_p), int(t.size), int(bool(src_is_nv12))))
 
     def logo_scan(self, scanw, scanh, thy, log_uvx=1, log_uvy=1):
         out = C.c_void_p()

@@ -980,6 +980,46 @@ int amtk_erase_logo_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo
   return 1;
 }
 
+int amtk_weave_frames(amtk_ctx* ctx, const amtk_clip* src, const amtk_clip* dst, int dst_frame0,
+                      const int32_t* top_idx, const int32_t* bottom_idx, int n, int src_is_nv12) {
+  if (!ctx || !top_idx || !bottom_idx) AMTK_FAIL("amtk_weave_frames: null argument");
+  if (!validate_clip(src, true) || !validate_clip(dst, true)) return 0;
+  if (!src->on_device || !dst->on_device) AMTK_FAIL("amtk_weave_frames: clips must be device resident");
+  if (src->width != dst->width || src->height != dst->height || src->bytes_per_sample != dst->bytes_per_sample ||
+      src->log_uvx != dst->log_uvx || src->log_uvy != dst->log_uvy)
+    AMTK_FAIL("amtk_weave_frames: source and destination formats differ");
+  if (n < 0 || dst_frame0 < 0 || dst_frame0 + n > dst->num_frames) AMTK_FAIL("frame range outside the clip");
+  for (int k = 0; k < n; ++k)
+    if (top_idx[k] < 0 || top_idx[k] >= src->num_frames || bottom_idx[k] < 0 || bottom_idx[k] >= src->num_frames)
+      AMTK_FAIL("amtk_weave_frames: source frame index outside the clip");
+  if (n == 0) return 1;
+  DevSelect ds(ctx); if (!ds.ok) return 0;
+  if (!ensure(&ctx->dout, &ctx->dout_bytes, (size_t)n * 2 * sizeof(int))) return 0;
+  int* didx = reinterpret_cast<int*>(ctx->dout);
+  AMTK_CUDA(cudaMemcpyAsync(didx, top_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  AMTK_CUDA(cudaMemcpyAsync(didx + n, bottom_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  WeaveJob j;
+  j.src = reinterpret_cast<const uint8_t*>(src->base); j.dst = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(dst->base));
+  j.sstride = src->frame_stride; j.dstride = dst->frame_stride;
+  j.s_offu = src->off_u; j.s_offv = src->off_v; j.d_offu = dst->off_u; j.d_offv = dst->off_v;
+  j.s_pitchY = src->pitch_y; j.s_pitchUV = src->pitch_uv; j.d_pitchY = dst->pitch_y; j.d_pitchUV = dst->pitch_uv;
+  j.bps = src->bytes_per_sample; j.nv12 = src_is_nv12 ? 1 : 0;
+  j.H = src->height; j.HC = src->height >> src->log_uvy;
+  j.row_bytes_y = src->width * j.bps; j.row_bytes_c = (src->width >> src->log_uvx) * j.bps;
+  j.top_idx = didx; j.bot_idx = didx + n; j.dst_frame0 = dst_frame0;
+  for (int k0 = 0; k0 < n; k0 += 32768) {
+    WeaveJob jj = j; jj.top_idx += k0; jj.bot_idx += k0; jj.dst_frame0 += k0;
+    const int nn = std::min(32768, n - k0);
+    const long long work = (long long)j.H * ((j.row_bytes_y + 15) / 16);
+    dim3 grid((unsigned)std::min<long long>((work + 255) / 256, 4096), 3, nn);
+    weave_kernel<<<grid, 256, 0, ctx->stream>>>(jj);
+    AMTK_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));      // index staging buffer is reused by later calls
+  return 1;
+}
+
 void amtk_calc_fade2(const float* records, int num_records, int num_frames, int n, float* ft, float* fb) {
   amtk::calc_fade2(records, num_records, num_frames, n, ft, fb);
 }

@@ -165,4 +165,49 @@ __global__ void __launch_bounds__(256) erase_logo_kernel(const EraseJob j) {
   }
 }
 
+// ---- AMTSource::MergeField (AMTSource.hpp:291-355): weave two decoded frames, optional NV12 chroma split ------------
+struct WeaveJob {
+  const uint8_t* src; uint8_t* dst;
+  long long sstride, dstride, s_offu, s_offv, d_offu, d_offv;
+  int s_pitchY, s_pitchUV, d_pitchY, d_pitchUV;   // BYTES
+  int row_bytes_y, row_bytes_c;                   // payload bytes per luma / chroma row (planar)
+  int H, HC, bps, nv12;
+  const int* top_idx; const int* bot_idx;         // device
+  int dst_frame0;
+};
+
+// grid (row blocks, 3 planes, frames); each thread moves 16 bytes of a row (tail bytes one by one)
+__global__ void __launch_bounds__(256) weave_kernel(const WeaveJob j) {
+  const int k = blockIdx.z, pl = blockIdx.y;
+  const int rows = pl ? j.HC : j.H;
+  const int rb = pl ? j.row_bytes_c : j.row_bytes_y;
+  const uint8_t* ft = j.src + (long long)j.top_idx[k] * j.sstride;
+  const uint8_t* fb = j.src + (long long)j.bot_idx[k] * j.sstride;
+  uint8_t* fd = j.dst + (long long)(j.dst_frame0 + k) * j.dstride;
+  const int vec_per_row = (rb + 15) / 16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * vec_per_row;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / vec_per_row), v = (int)(i - (long long)y * vec_per_row);
+    const uint8_t* fs = (y & 1) ? fb : ft;             // even rows from `top`, odd rows from `bottom` (Copy1 :292-302)
+    const int nbytes = min(16, rb - v * 16);
+    if (pl == 0 || !j.nv12) {
+      const uint8_t* s = fs + (pl == 0 ? 0 : (pl == 1 ? j.s_offu : j.s_offv)) + (long long)y * (pl ? j.s_pitchUV : j.s_pitchY) + v * 16;
+      uint8_t* d = fd + (pl == 0 ? 0 : (pl == 1 ? j.d_offu : j.d_offv)) + (long long)y * (pl ? j.d_pitchUV : j.d_pitchY) + v * 16;
+      if (nbytes == 16 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0)
+        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+      else
+        for (int b = 0; b < nbytes; ++b) d[b] = s[b];
+    } else {
+      // NV12: interleaved UV row -> U (pl 1) or V (pl 2) samples (Copy2 :304-321)
+      const uint8_t* s = fs + j.s_offu + (long long)y * j.s_pitchUV;
+      uint8_t* d = fd + (pl == 1 ? j.d_offu : j.d_offv) + (long long)y * j.d_pitchUV + v * 16;
+      const int comp = pl - 1;
+      for (int b = 0; b < nbytes; b += j.bps) {
+        const int xs = (v * 16 + b) / j.bps;           // sample index in the row
+        for (int q = 0; q < j.bps; ++q) d[b + q] = s[(xs * 2 + comp) * j.bps + q];
+      }
+    }
+  }
+}
+
 }  // namespace amtk

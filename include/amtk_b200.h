@@ -186,6 +186,17 @@ AMTK_API int amtk_scan_logo(amtk_ctx* ctx, const amtk_clip* clip, int service_id
                             int imgx, int imgy, int w, int h, int thy, int max_frames, amtk_logo_analyze_cb cb);
 
 /* ---------------------------------------------------------------------------------------------
+ * Frame ingest: field weave + NV12 split on the device (replaces AMTSource::MergeField / Copy1 / Copy2,
+ * AMTSource.hpp:291-355, used by MakeFrame :357-366 for half-delay (BFF / repeat-field) sources,
+ * StreamReform.hpp:890-903).  dst frame k (k = 0..n-1, starting at dst_frame0) takes its EVEN rows (luma and chroma)
+ * from src frame top_idx[k] and its ODD rows from src frame bottom_idx[k]; with src_is_nv12 the source chroma is one
+ * interleaved UV plane at off_u (pitch_uv bytes per row) that is split into dst's U and V planes.
+ * Both clips must be device resident, same size and sample format.  top_idx/bottom_idx are host pointers.
+ * ------------------------------------------------------------------------------------------- */
+AMTK_API int amtk_weave_frames(amtk_ctx* ctx, const amtk_clip* src, const amtk_clip* dst, int dst_frame0,
+                               const int32_t* top_idx, const int32_t* bottom_idx, int n, int src_is_nv12);
+
+/* ---------------------------------------------------------------------------------------------
  * Logo erase (replaces AMTEraseLogo::Delogo on Y,U,V, LogoScan.hpp:1248-1261,1374-1397), in place on a
  * device-resident or host clip.  fades float[nframes][2] = fadeT,fadeB per frame (host pointer).
  * ------------------------------------------------------------------------------------------- */

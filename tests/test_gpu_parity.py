@@ -366,3 +366,41 @@ def test_scan_logo_pipeline(ctx, oracle, tmp_path):
         ctx.scan_logo(clip, dst, sx, sy, sw, sh, thy, maxf, cb=lambda *a: False)
     with pytest.raises(ab.AmtkError, match="Insufficient logo frames"):
         ctx.scan_logo(clip, dst, sx, sy, sw, sh, 0, maxf)
+
+
+def test_weave_frames_matches_mergefield(ctx):
+    """AMTSource::MergeField/Copy1/Copy2 (AMTSource.hpp:291-355): even rows from `top`, odd rows from `bottom`,
+    planar and NV12 sources, 8- and 16-bit."""
+    w, h, n = 208, 72, 6
+    src8 = synth.make_frames(0, n, w, h, device="cuda", mode="interlaced")
+    top = np.array([0, 1, 2, 3, 4, 5], np.int32)
+    bot = np.array([1, 2, 3, 4, 5, 5], np.int32)          # half-delay: bottom field of the next decoded frame
+    for bits in (8, 10):
+        src = src8 if bits == 8 else (src8.to(torch.int32) * 4 + 2).to(torch.int16).contiguous()
+        dst = torch.zeros_like(src)
+        ctx.weave_frames(ab.yv12_clip(src, w, h, n, True, bits), ab.yv12_clip(dst, w, h, n, True, bits), top, bot)
+        a = src.cpu().numpy(); a = a if bits == 8 else a.view(np.uint16)
+        g = dst.cpu().numpy(); g = g if bits == 8 else g.view(np.uint16)
+        ysz, csz = w * h, (w // 2) * (h // 2)
+        for k in range(n):
+            for (o, rows, cols) in ((0, h, w), (ysz, h // 2, w // 2), (ysz + csz, h // 2, w // 2)):
+                t = a[top[k], o:o + rows * cols].reshape(rows, cols)
+                b = a[bot[k], o:o + rows * cols].reshape(rows, cols)
+                exp = t.copy(); exp[1::2] = b[1::2]
+                assert np.array_equal(g[k, o:o + rows * cols].reshape(rows, cols), exp), (bits, k, o)
+    # NV12 source: interleaved UV plane split into U and V
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    a = src8.cpu().numpy()
+    nv = a.copy()
+    uv = np.stack([a[:, ysz:ysz + csz], a[:, ysz + csz:]], axis=2).reshape(n, 2 * csz)
+    nv[:, ysz:] = uv
+    nv_t = torch.from_numpy(nv).cuda()
+    sclip = ab.yv12_clip(nv_t, w, h, n, True)
+    sclip.pitch_uv = w                                     # interleaved UV rows are `width` bytes long
+    dst = torch.zeros_like(src8)
+    ctx.weave_frames(sclip, ab.yv12_clip(dst, w, h, n, True), top, bot, src_is_nv12=True)
+    ref = torch.zeros_like(src8)
+    ctx.weave_frames(ab.yv12_clip(src8, w, h, n, True), ab.yv12_clip(ref, w, h, n, True), top, bot)
+    assert torch.equal(dst, ref)
+    with pytest.raises(ab.AmtkError, match="index outside"):
+        ctx.weave_frames(ab.yv12_clip(src8, w, h, n, True), ab.yv12_clip(dst, w, h, n, True), top, bot + 1)
