@@ -242,7 +242,7 @@ static const CombVariant* comb_variants(int* n) {
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }
-static int g_comb_force_generic = 0;
+static int g_comb_force_generic = 0, g_comb_merge_uv = 1;
 static int g_comb_strip = 8, g_comb_stages = 3, g_comb_R = 0, g_comb_ctas_per_sm = 0, g_comb_acc = 0, g_comb_l2 = 128;   // tuning knobs (env AMTK_COMB_*)
 
 // rows per run: the R in {15,16,17} that wastes the fewest rows over luma + chroma (1080/540 -> 17, 720/360 -> 15)
@@ -296,33 +296,44 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   if (!V) AMTK_FAIL("comb: no kernel variant for the requested AMTK_COMB_* settings");
   CombArgs args;
   memset(&args, 0, sizeof(args));
+  // Chroma width 960 = 7.5 tiles: the 64-pixel remainders of U and V share ONE tile (two half-width TMA boxes)
+  // instead of two half-empty ones.
+  const int wC = clip->width >> clip->log_uvx;
+  const int rem = wC % kCombTW;
+  const bool merge_uv = g_comb_merge_uv && rem > 0 && rem <= kCombTW / 2 && (V->boxH * (kCombTW / 2)) % 128 == 0;
   int tile0 = 0;
-  for (int pl = 0; pl < 3; ++pl) {
+  for (int pl = 0; pl < 4; ++pl) {
     CombPlane& P = args.plane[pl];
-    P.W = pl ? (clip->width >> clip->log_uvx) : clip->width;
-    P.H = pl ? hC : hY;
+    const bool chroma = pl != 0;
+    P.W = chroma ? wC : clip->width;
+    P.H = chroma ? hC : hY;
     P.tilesX = (P.W + kCombTW - 1) / kCombTW; P.tilesY = (P.H + V->TH - 1) / V->TH;
+    if (merge_uv && (pl == 1 || pl == 2)) P.tilesX -= 1;           // remainder column handled by the pseudo plane
+    if (pl == 3) { P.tilesX = merge_uv ? 1 : 0; if (!merge_uv) P.tilesY = 0; }
     P.tile0 = tile0; tile0 += P.tilesX * P.tilesY;
-    P.cls = pl ? 1 : 0;
-    const int thM = pl ? prm->th_move_c : prm->th_move_y;
-    const int thS = pl ? prm->th_shima_c : prm->th_shima_y, thL = pl ? prm->th_lshima_c : prm->th_lshima_y;
+    P.cls = chroma ? 1 : 0;
+    const int thM = chroma ? prm->th_move_c : prm->th_move_y;
+    const int thS = chroma ? prm->th_shima_c : prm->th_shima_y, thL = chroma ? prm->th_lshima_c : prm->th_lshima_y;
     P.thM = (unsigned)(0x80 - thM) * 0x01010101u;
     P.thS = (unsigned)thS * 0x00010001u;       // integer k in [1,2047] IS the fp16 bit pattern of k*2^-24
     P.thL = (unsigned)thL * 0x00010001u;
+    if (pl == 3) break;
     const long long off = pl == 0 ? 0 : (pl == 1 ? clip->off_u : clip->off_v);
     const int pitch = pl ? clip->pitch_uv : clip->pitch_y;
     cuuint64_t gdim[3] = { (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)win.count };
     cuuint64_t gstr[2] = { (cuuint64_t)pitch, (cuuint64_t)clip->frame_stride };
-    cuuint32_t box[3] = { (cuuint32_t)kCombTW, (cuuint32_t)V->boxH, 1u };
     cuuint32_t estr[3] = { 1u, 1u, 1u };
-    CUresult r = ctx->encode_tiled(&args.map[pl], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
-                                   const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   g_comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : g_comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
-                                   g_comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) AMTK_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    const CUtensorMapL2promotion promo = g_comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : g_comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                         g_comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    for (int half = 0; half < (pl && merge_uv ? 2 : 1); ++half) {
+      cuuint32_t box[3] = { (cuuint32_t)(half ? kCombTW / 2 : kCombTW), (cuuint32_t)V->boxH, 1u };
+      CUtensorMap* m = half ? &args.map_half[pl - 1] : &args.map[pl];
+      CUresult r = ctx->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) AMTK_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    }
   }
+  args.half_x = wC - rem;
   const int ntiles = tile0;
   const int nf = hi - lo;
   // ---- static partition of (tile, frame) pairs over the resident CTAs: tile-major, frame-minor, equal shares.
@@ -427,6 +438,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_CTAS")) g_comb_ctas_per_sm = atoi(e);
   if (const char* e = getenv("AMTK_COMB_ACC")) g_comb_acc = atoi(e);
   if (const char* e = getenv("AMTK_COMB_GENERIC")) g_comb_force_generic = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_MERGE_UV")) g_comb_merge_uv = atoi(e);
   if (const char* e = getenv("AMTK_COMB_L2")) g_comb_l2 = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }

@@ -59,8 +59,10 @@ struct CombSegment {        // a run of frames of one tile, processed by one CTA
 };
 
 struct CombArgs {
-  CUtensorMap map[3];       // 3-D (x, y, frame) u8 views of the Y, U, V planes of the device window
-  CombPlane plane[3];
+  CUtensorMap map[3];       // 3-D (x, y, frame) u8 views of the Y, U, V planes of the device window (box 128 x BOXH)
+  CUtensorMap map_half[2];  // U and V again with a 64-byte wide box: the two 64-pixel remainders share one tile
+  CombPlane plane[4];       // [3] = pseudo plane of the merged U|V remainder tiles (tilesX = 1), when used
+  int half_x;               // x of the remainder columns in the chroma planes
   const CombSegment* segs;
   const int* seg_start;     // [gridDim.x + 1]
   int* counts;              // [nframes_out][12]
@@ -101,7 +103,7 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t d, uint32_t kM) {
   return (((d & 0x7F7F7F7Fu) + kM) | d) & 0x80808080u;
 }
 
-template <typename Cfg, bool EDGE>
+template <typename Cfg, bool EDGE, int PITCH>
 __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
                                                int y_first /* global y of this thread's first row */,
                                                const uint32_t* __restrict__ th_rows /* EDGE: [2][R] thresholds of this run */,
@@ -118,14 +120,14 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
 
   RawRow<STRIP> raw_c, raw_n, rtmp;
   rtmp.load(cur);                 HRow<NQ> h0 = bytes_to_half<STRIP>(rtmp);
-  rtmp.load(cur + kCombTW);       HRow<NQ> h1 = bytes_to_half<STRIP>(rtmp);
-  raw_c.load(cur + 2 * kCombTW);  HRow<NQ> h2 = bytes_to_half<STRIP>(raw_c);     // centre row of j=0
-  raw_n.load(cur + 3 * kCombTW);  HRow<NQ> h3 = bytes_to_half<STRIP>(raw_n);
+  rtmp.load(cur + PITCH);       HRow<NQ> h1 = bytes_to_half<STRIP>(rtmp);
+  raw_c.load(cur + 2 * PITCH);  HRow<NQ> h2 = bytes_to_half<STRIP>(raw_c);     // centre row of j=0
+  raw_n.load(cur + 3 * PITCH);  HRow<NQ> h3 = bytes_to_half<STRIP>(raw_n);
 #pragma unroll
   for (int j = 0; j < R; ++j) {
-    RawRow<STRIP> raw_nn; raw_nn.load(cur + (j + 4) * kCombTW);
+    RawRow<STRIP> raw_nn; raw_nn.load(cur + (j + 4) * PITCH);
     const HRow<NQ> h4 = bytes_to_half<STRIP>(raw_nn);
-    RawRow<STRIP> pv; pv.load(prev + (j + 2) * kCombTW);
+    RawRow<STRIP> pv; pv.load(prev + (j + 2) * PITCH);
     const int f = j & 1;          // accumulator slot; mapped to the field parity after the loop
     // rows y < 2 and y >= H-2 have no comb response (spec): edge tiles read per-row thresholds (infinite there)
     // from a small shared table built once per segment -- two LDS instead of compare/select on the ALU pipe
@@ -201,9 +203,10 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
   const int seg_lo = a.seg_start[blockIdx.x], seg_hi = a.seg_start[blockIdx.x + 1];
   for (int si = seg_lo; si < seg_hi; ++si) {
     const CombSegment seg = a.segs[si];
-    const int pl = (seg.tile >= a.plane[2].tile0) ? 2 : (seg.tile >= a.plane[1].tile0) ? 1 : 0;
+    const int pl = (seg.tile >= a.plane[3].tile0) ? 3 : (seg.tile >= a.plane[2].tile0) ? 2 : (seg.tile >= a.plane[1].tile0) ? 1 : 0;
     const CombPlane& P = a.plane[pl];
-    const CUtensorMap* map = &a.map[pl];
+    const bool merged = pl == 3;                     // strips 0..7 <- U remainder, strips 8..15 <- V remainder
+    const CUtensorMap* map = &a.map[merged ? 0 : pl];
     const int lt = seg.tile - P.tile0;
     const int ty = lt / P.tilesX, tx = lt - ty * P.tilesX;
     const int x0 = tx * kCombTW, y0 = ty * Cfg::TH;
@@ -219,13 +222,18 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
       const int st = g % S;
       const int fr = (j == 0) ? fprev : seg.fbegin + j - 1;
       mbar_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
-      tma_load_3d(tiles + st * Cfg::STAGE_BYTES, map, &full_bar[st], x0, y0 - 2, fr);
+      if (!merged) {
+        tma_load_3d(tiles + st * Cfg::STAGE_BYTES, map, &full_bar[st], x0, y0 - 2, fr);
+      } else {                                       // two half-width boxes, one behind the other in the stage
+        tma_load_3d(tiles + st * Cfg::STAGE_BYTES, &a.map_half[0], &full_bar[st], a.half_x, y0 - 2, fr);
+        tma_load_3d(tiles + st * Cfg::STAGE_BYTES + Cfg::STAGE_BYTES / 2, &a.map_half[1], &full_bar[st], a.half_x, y0 - 2, fr);
+      }
     };
     if (tid == 0) {
       const int pro = nloads < S ? nloads : S;
       for (int j = 0; j < pro; ++j) issue(j);
     }
-    if (edge) {                                      // (re)build the per-row threshold table of this tile
+    if (edge || merged) {                            // (re)build the per-row threshold table of this tile
       for (int i = tid; i < Cfg::RUNS * Cfg::R; i += Cfg::THREADS) {
         const int y = y0 + i;
         const bool ok = y >= 2 && y < P.H - 2;
@@ -239,13 +247,20 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
       const uint32_t g = gload + (uint32_t)k;
       const int st = g % S, stp = (g - 1) % S;
       mbar_wait(&full_bar[st], (g / S) & 1u);
-      const uint8_t* cur = tiles + st * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
-      const uint8_t* prv = tiles + stp * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
       uint32_t vS = 0, vL = 0, vM = 0;
-      if (!edge) {
-        comb_tile_rows<Cfg, false>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
-      } else if (rows_live) {
-        comb_tile_rows<Cfg, true>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+      if (!merged) {
+        const uint8_t* cur = tiles + st * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
+        const uint8_t* prv = tiles + stp * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
+        if (!edge) {
+          comb_tile_rows<Cfg, false, kCombTW>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
+        } else if (rows_live) {
+          comb_tile_rows<Cfg, true, kCombTW>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+        }
+      } else if (rows_live) {                        // half-width sub-tiles: row pitch 64 bytes
+        constexpr int HP = kCombTW / 2, HTPR = HP / Cfg::STRIP;
+        const int off = (strip / HTPR) * (Cfg::STAGE_BYTES / 2) + (run * Cfg::R) * HP + (strip % HTPR) * Cfg::STRIP;
+        comb_tile_rows<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off, y_first,
+                                      &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
       }
       vS = __reduce_add_sync(0xFFFFFFFFu, vS);
       vL = __reduce_add_sync(0xFFFFFFFFu, vL);
