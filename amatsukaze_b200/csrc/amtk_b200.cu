@@ -281,7 +281,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
       CombGenericArgs gg = g;
       gg.first_frame = g.first_frame + f0; gg.prev_of_first = f0 ? gg.first_frame - 1 : g.prev_of_first;
       gg.nframes = std::min(16384, hi - lo - f0); gg.counts = g.counts + (size_t)f0 * 12;
-      dim3 grid((g.W[0] + 31) / 32, (g.H[0] + 7) / 8, gg.nframes * 3);
+      dim3 grid((g.W[0] + kGenTW - 1) / kGenTW, (g.H[0] + kGenTH - 1) / kGenTH, gg.nframes * 3);
       if (bps == 1) comb_generic_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(gg);
       else comb_generic_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(gg);
       AMTK_CUDA(cudaGetLastError());

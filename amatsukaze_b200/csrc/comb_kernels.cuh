@@ -298,36 +298,52 @@ struct CombGenericArgs {
   int* counts;             // row 0 = first_frame
 };
 
+// block = 8 warps, tile = 128 columns x 128 rows of one plane of one frame: warp w walks rows [16w, 16w+16) of the
+// tile, lane l owns columns l, l+32, l+64, l+96 with a 5-row sliding window in registers (2 loads per pixel: current
+// and previous frame).  Counters: registers -> REDUX -> shared -> 6 global atomics per block.
+constexpr int kGenTW = 128, kGenTH = 128;
 template <typename pixel_t>
 __global__ void __launch_bounds__(256) comb_generic_kernel(const CombGenericArgs a) {
+  __shared__ int blk[6];
   const int pl = blockIdx.z % 3, f = blockIdx.z / 3;
   const int W = a.W[pl], H = a.H[pl], pitch = a.pitch[pl];
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);          // one warp = one row segment => uniform field parity
-  if (blockIdx.x * 32 >= W || blockIdx.y * 8 >= H) return;
+  const int x0 = blockIdx.x * kGenTW, y0 = blockIdx.y * kGenTH;
+  if (x0 >= W || y0 >= H) return;                              // block-uniform
+  if (threadIdx.x < 6) blk[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cur_f = a.first_frame + f, prev_f = f == 0 ? a.prev_of_first : cur_f - 1;
   const pixel_t* cur = reinterpret_cast<const pixel_t*>(a.base + (long long)cur_f * a.frame_stride + a.off[pl]);
   const pixel_t* prv = reinterpret_cast<const pixel_t*>(a.base + (long long)prev_f * a.frame_stride + a.off[pl]);
-  bool mv = false, sh = false, lsh = false;
-  if (x < W && y < H) {
-    const long long o = x + (long long)y * pitch;
-    const int c = cur[o];
-    int d = c - (int)prv[o]; d = d < 0 ? -d : d;
-    mv = d >= a.thM[pl];
-    if (y >= 2 && y < H - 2) {
-      int v = (int)cur[o - 2 * (long long)pitch] + 4 * c + (int)cur[o + 2 * (long long)pitch]
-              - 3 * ((int)cur[o - pitch] + (int)cur[o + pitch]);
-      v = v < 0 ? -v : v;
-      sh = v >= a.thS[pl]; lsh = v >= a.thL[pl];
+  const int thM = a.thM[pl], thS = a.thS[pl], thL = a.thL[pl];
+  int cnt[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };                // [field][move, shima, lshima]
+  const int ya = y0 + warp * 16, yb = min(ya + 16, H);
+#pragma unroll
+  for (int cg = 0; cg < 4; ++cg) {
+    const int x = x0 + lane + 32 * cg;
+    if (x >= W || ya >= H) continue;
+    auto px = [&](int y) -> int { return (y >= 0 && y < H) ? (int)cur[x + (long long)y * pitch] : 0; };
+    int r0 = px(ya - 2), r1 = px(ya - 1), r2 = px(ya), r3 = px(ya + 1);
+    for (int y = ya; y < yb; ++y) {
+      const int r4 = px(y + 2);
+      int d = r2 - (int)prv[x + (long long)y * pitch]; d = d < 0 ? -d : d;
+      const int fld = y & 1;
+      cnt[fld][0] += d >= thM;
+      if (y >= 2 && y < H - 2) {
+        int v = r0 + 4 * r2 + r4 - 3 * (r1 + r3); v = v < 0 ? -v : v;
+        cnt[fld][1] += v >= thS; cnt[fld][2] += v >= thL;
+      }
+      r0 = r1; r1 = r2; r2 = r3; r3 = r4;
     }
   }
-  const unsigned bm = __ballot_sync(0xFFFFFFFFu, mv), bs = __ballot_sync(0xFFFFFFFFu, sh), bl = __ballot_sync(0xFFFFFFFFu, lsh);
-  if ((threadIdx.x & 31) == 0 && y < H) {
-    int* o = a.counts + (size_t)f * 12 + (pl ? 6 : 0) + (y & 1) * 3;
-    if (bm) atomicAdd(o + 0, __popc(bm));
-    if (bs) atomicAdd(o + 1, __popc(bs));
-    if (bl) atomicAdd(o + 2, __popc(bl));
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int v = __reduce_add_sync(0xFFFFFFFFu, cnt[k / 3][k % 3]);
+    if (lane == 0 && v) atomicAdd(&blk[k], v);
   }
+  __syncthreads();
+  if (threadIdx.x < 6 && blk[threadIdx.x])
+    atomicAdd(a.counts + (size_t)f * 12 + (pl ? 6 : 0) + threadIdx.x, blk[threadIdx.x]);    // [field][metric] order = k
 }
 
 }  // namespace amtk
