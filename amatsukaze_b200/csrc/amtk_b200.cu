@@ -242,7 +242,7 @@ static const CombVariant* comb_variants(int* n) {
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }
-static int g_comb_force_generic = 0, g_comb_merge_uv = 1;
+static int g_comb_force_generic = 0, g_comb_merge_uv = 1, g_comb_part = -1;   // part: -1 auto, 0 equal-share, 1 lock-step
 static int g_comb_strip = 8, g_comb_stages = 3, g_comb_R = 0, g_comb_ctas_per_sm = 0, g_comb_acc = 0, g_comb_l2 = 128;   // tuning knobs (env AMTK_COMB_*)
 
 // rows per run: the R in {15,16,17} that wastes the fewest rows over luma + chroma (1080/540 -> 17, 720/360 -> 15)
@@ -345,9 +345,23 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
   if (g_comb_ctas_per_sm > 0) occ = std::min(occ, g_comb_ctas_per_sm);
   const long long total = (long long)ntiles * nf;
-  const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, total);
+  int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, total);
   std::vector<CombSegment> segs;
+  // "lock-step" partition: every tile is cut into the same C frame ranges, so neighbouring tiles stream the same
+  // frames at the same time and share halo rows / straddled 128-byte lines through L2.  Used when the plane pitch
+  // makes tile rows straddle lines (pitch % 128 != 0 on luma) or when forced; costs a few idle CTA slots.
+  const int chunks = std::max(1, std::min(nf, grid / std::max(1, ntiles)));
+  const bool lockstep = g_comb_part == 1 || (g_comb_part < 0 && (clip->pitch_y % 128) != 0 && chunks * ntiles * 10 >= grid * 9);
+  if (lockstep) grid = chunks * ntiles;
   std::vector<int> seg_start((size_t)grid + 1, 0);
+  if (lockstep) {
+    for (int b = 0; b < grid; ++b) {                 // CTA b = (chunk c, tile t), tile-minor so that co-resident CTAs are neighbours
+      const int c = b / ntiles, t = b % ntiles;
+      const int f0 = (int)((long long)nf * c / chunks), f1 = (int)((long long)nf * (c + 1) / chunks);
+      seg_start[b] = (int)segs.size();
+      if (f1 > f0) segs.push_back(CombSegment{ t, lo - win.first + f0, lo - win.first + f1 });
+    }
+  } else
   for (int b = 0; b < grid; ++b) {
     const long long lo_i = total * b / grid, hi_i = total * (b + 1) / grid;     // [lo_i, hi_i) of the tile-major order
     seg_start[b] = (int)segs.size();
@@ -439,6 +453,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_ACC")) g_comb_acc = atoi(e);
   if (const char* e = getenv("AMTK_COMB_GENERIC")) g_comb_force_generic = atoi(e);
   if (const char* e = getenv("AMTK_COMB_MERGE_UV")) g_comb_merge_uv = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_PART")) g_comb_part = atoi(e);
   if (const char* e = getenv("AMTK_COMB_L2")) g_comb_l2 = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }
