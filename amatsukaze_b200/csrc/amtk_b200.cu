@@ -209,9 +209,10 @@ static bool roi_inside(const amtk::HostLogo& full, const amtk_clip* clip, int pi
 // comb launch
 // ---------------------------------------------------------------------------------------------------------
 static int comb_thresholds_ok(const amtk_comb_params* p, int bytes_per_sample) {
-  if (bytes_per_sample == 2) {       // generic integer kernel: any positive threshold
+  if (bytes_per_sample == 2) {
     const int all[6] = { p->th_move_y, p->th_shima_y, p->th_lshima_y, p->th_move_c, p->th_shima_c, p->th_lshima_c };
     for (int v : all) if (v < 1) { set_error("comb: thresholds must be >= 1"); return 0; }
+    if (p->th_move_y > 32768 || p->th_move_c > 32768) { set_error("comb: th_move must be in [1,32768] for 16-bit samples"); return 0; }
     return 1;
   }
   const int m[2] = { p->th_move_y, p->th_move_c };
@@ -224,14 +225,18 @@ static int comb_thresholds_ok(const amtk_comb_params* p, int bytes_per_sample) {
 // Everything the host needs to know about one compiled comb-kernel variant.
 struct CombVariant {
   int R, strip, stages, acc, TH, boxH, threads, smem;
-  void (*kernel)(const CombArgs);
+  void (*kernel)(const CombArgs);        // 8-bit samples
+  void (*kernel16)(const CombArgs);      // 16-bit samples (only for the default variants; else NULL)
 };
 template <typename Cfg> static CombVariant make_variant() {
-  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::ACC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_u8_kernel<Cfg> };
+  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::ACC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_tma_kernel<Cfg, 1>, nullptr };
+}
+template <typename Cfg> static CombVariant make_variant16() {     // 8-byte strips: 8 px of u8 or 4 px of u16
+  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::ACC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_tma_kernel<Cfg, 1>, comb_tma_kernel<Cfg, 2> };
 }
 static const CombVariant* comb_variants(int* n) {
   static const CombVariant v[] = {
-    make_variant<CombCfg<15, 8, 3, 0>>(), make_variant<CombCfg<16, 8, 3, 0>>(), make_variant<CombCfg<17, 8, 3, 0>>(),
+    make_variant16<CombCfg<15, 8, 3, 0>>(), make_variant16<CombCfg<16, 8, 3, 0>>(), make_variant16<CombCfg<17, 8, 3, 0>>(),
     make_variant<CombCfg<15, 8, 3, 1>>(), make_variant<CombCfg<16, 8, 3, 1>>(), make_variant<CombCfg<17, 8, 3, 1>>(),
     make_variant<CombCfg<15, 8, 3, 2>>(), make_variant<CombCfg<16, 8, 3, 2>>(), make_variant<CombCfg<17, 8, 3, 2>>(),
     make_variant<CombCfg<17, 8, 4, 0>>(), make_variant<CombCfg<17, 8, 4, 1>>(), make_variant<CombCfg<17, 8, 4, 2>>(),
@@ -260,7 +265,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
                        const amtk_comb_params* prm, int* dcounts, int out_row0) {
   const bool tma_layout = !((clip->frame_stride & 15) || (clip->pitch_y & 15) || (clip->pitch_uv & 15) || (clip->off_u & 15) ||
                             (clip->off_v & 15) || (reinterpret_cast<uintptr_t>(win.dev_base) & 15));
-  if (clip->bytes_per_sample != 1 || !tma_layout || !ctx->encode_tiled || g_comb_force_generic) {
+  if (!tma_layout || !ctx->encode_tiled || g_comb_force_generic) {
     // generic kernel: any sample size / pitch (DESIGN.md 3.1 "fallback")
     CombGenericArgs g;
     g.base = win.dev_base; g.frame_stride = clip->frame_stride;
@@ -294,29 +299,38 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
   for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == g_comb_strip && vars[i].stages == g_comb_stages && vars[i].acc == g_comb_acc) V = &vars[i];
   if (!V) AMTK_FAIL("comb: no kernel variant for the requested AMTK_COMB_* settings");
+  const int bps = clip->bytes_per_sample;
+  if (bps == 2 && !V->kernel16) AMTK_FAIL("comb: the selected AMTK_COMB_* variant has no 16-bit kernel");
+  const int twe = kCombTW / bps;                 // samples per tile row
   CombArgs args;
   memset(&args, 0, sizeof(args));
   // Chroma width 960 = 7.5 tiles: the 64-pixel remainders of U and V share ONE tile (two half-width TMA boxes)
   // instead of two half-empty ones.
   const int wC = clip->width >> clip->log_uvx;
-  const int rem = wC % kCombTW;
-  const bool merge_uv = g_comb_merge_uv && rem > 0 && rem <= kCombTW / 2 && (V->boxH * (kCombTW / 2)) % 128 == 0;
+  const int rem = wC % twe;
+  const bool merge_uv = g_comb_merge_uv && rem > 0 && rem <= twe / 2 && (V->boxH * (kCombTW / 2)) % 128 == 0;
   int tile0 = 0;
   for (int pl = 0; pl < 4; ++pl) {
     CombPlane& P = args.plane[pl];
     const bool chroma = pl != 0;
     P.W = chroma ? wC : clip->width;
     P.H = chroma ? hC : hY;
-    P.tilesX = (P.W + kCombTW - 1) / kCombTW; P.tilesY = (P.H + V->TH - 1) / V->TH;
+    P.tilesX = (P.W + twe - 1) / twe; P.tilesY = (P.H + V->TH - 1) / V->TH;
     if (merge_uv && (pl == 1 || pl == 2)) P.tilesX -= 1;           // remainder column handled by the pseudo plane
     if (pl == 3) { P.tilesX = merge_uv ? 1 : 0; if (!merge_uv) P.tilesY = 0; }
     P.tile0 = tile0; tile0 += P.tilesX * P.tilesY;
     P.cls = chroma ? 1 : 0;
     const int thM = chroma ? prm->th_move_c : prm->th_move_y;
     const int thS = chroma ? prm->th_shima_c : prm->th_shima_y, thL = chroma ? prm->th_lshima_c : prm->th_lshima_y;
-    P.thM = (unsigned)(0x80 - thM) * 0x01010101u;
-    P.thS = (unsigned)thS * 0x00010001u;       // integer k in [1,2047] IS the fp16 bit pattern of k*2^-24
-    P.thL = (unsigned)thL * 0x00010001u;
+    if (bps == 1) {
+      P.thM = (unsigned)(0x80 - thM) * 0x01010101u;
+      P.thS = (unsigned)thS * 0x00010001u;       // integer k in [1,2047] IS the fp16 bit pattern of k*2^-24
+      P.thL = (unsigned)thL * 0x00010001u;
+    } else {
+      P.thM = (unsigned)(0x8000 - thM) * 0x00010001u;
+      const float fs = (float)thS, fl = (float)thL;
+      memcpy(&P.thS, &fs, 4); memcpy(&P.thL, &fl, 4);
+    }
     if (pl == 3) break;
     const long long off = pl == 0 ? 0 : (pl == 1 ? clip->off_u : clip->off_v);
     const int pitch = pl ? clip->pitch_uv : clip->pitch_y;
@@ -326,9 +340,9 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     const CUtensorMapL2promotion promo = g_comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : g_comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
                                          g_comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     for (int half = 0; half < (pl && merge_uv ? 2 : 1); ++half) {
-      cuuint32_t box[3] = { (cuuint32_t)(half ? kCombTW / 2 : kCombTW), (cuuint32_t)V->boxH, 1u };
+      cuuint32_t box[3] = { (cuuint32_t)(half ? twe / 2 : twe), (cuuint32_t)V->boxH, 1u };
       CUtensorMap* m = half ? &args.map_half[pl - 1] : &args.map[pl];
-      CUresult r = ctx->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
+      CUresult r = ctx->encode_tiled(m, bps == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) AMTK_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     }
@@ -340,8 +354,9 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   // A tile-frame costs the same wherever it lies (the kernel is issue/latency bound per warp, and tile shapes are
   // chosen so that bands are full), so equal counts = equal time; each CTA touches at most ~2 tiles.
   int occ = 0;
-  AMTK_CUDA(cudaFuncSetAttribute(V->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
-  AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, V->kernel, V->threads, V->smem));
+  void (*kern)(const CombArgs) = bps == 1 ? V->kernel : V->kernel16;
+  AMTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
+  AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, V->threads, V->smem));
   if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
   if (g_comb_ctas_per_sm > 0) occ = std::min(occ, g_comb_ctas_per_sm);
   const long long total = (long long)ntiles * nf;
@@ -391,7 +406,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     else { AMTK_CUDA(cudaEventCreate(&ev.first)); AMTK_CUDA(cudaEventCreate(&ev.second)); }
     AMTK_CUDA(cudaEventRecord(ev.first, ctx->stream));
   }
-  V->kernel<<<grid, V->threads, V->smem, ctx->stream>>>(args);
+  kern<<<grid, V->threads, V->smem, ctx->stream>>>(args);
   AMTK_CUDA(cudaGetLastError());
   if (ctx->timing) { AMTK_CUDA(cudaEventRecord(ev.second, ctx->stream)); ctx->timing_events.push_back(ev); }
   ctx->launches += 1;

@@ -46,11 +46,11 @@ struct CombCfg {
 };
 
 struct CombPlane {
-  int W, H;                 // plane size in pixels
+  int W, H;                 // plane size in samples
   int tilesX, tilesY;
   int tile0;                // first tile id of this plane
   int cls;                  // 0 = Y, 1 = C
-  unsigned thM, thS, thL;   // thM: SWAR byte constant (0x80-thM)*0x01010101; thS/thL: packed half2 bit patterns
+  unsigned thM, thS, thL;   // u8: thM = (0x80-thM)*0x01010101, thS/thL = fp16x2 bit patterns; u16: (0x8000-thM)*0x00010001, fp32 bits
 };
 
 struct CombSegment {        // a run of frames of one tile, processed by one CTA
@@ -176,8 +176,72 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
   oM = flip ? (m1 | (m0 << 16)) : (m0 | (m1 << 16));
 }
 
-template <typename Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_constant__ CombArgs a) {
+// ---------------------------------------------------------------------------------------------------------
+// 16-bit samples (YUV420P10/12/16): same tile machinery, 4 pixels (8 bytes) per thread-row.  The 5-tap response of
+// 16-bit samples (<= 6*65535) is exact in fp32, so the stencil runs as FADD/FFMA on floats made from the u16 lanes
+// with one PRMT (0x4B00 high half = 2^23 + x) and one FADD (-2^23) each; FSET.BF.GE with |x| thresholds, float
+// counters (exact below 2^24); the inter-frame difference stays integer: VIMNMX3.U16x2 max/min, SWAR compare, IDP.4A.
+// kM = (0x8000 - thM) * 0x00010001 (1 <= thM <= 32768); thS/thL are float bit patterns.
+// ---------------------------------------------------------------------------------------------------------
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 u16x4_to_float(uint2 raw) {
+  F4 r;
+  r.v[0] = __uint_as_float(__byte_perm(raw.x, 0x4B000000u, 0x7410)) - 8388608.0f;
+  r.v[1] = __uint_as_float(__byte_perm(raw.x, 0x4B000000u, 0x7432)) - 8388608.0f;
+  r.v[2] = __uint_as_float(__byte_perm(raw.y, 0x4B000000u, 0x7410)) - 8388608.0f;
+  r.v[3] = __uint_as_float(__byte_perm(raw.y, 0x4B000000u, 0x7432)) - 8388608.0f;
+  return r;
+}
+__device__ __forceinline__ uint32_t halves_ge(uint32_t a, uint32_t b, uint32_t kM) {   // |a-b| >= thM per 16-bit lane -> bit 15/31
+  const uint32_t d = __vimax3_u16x2(a, b, 0u) - __vimin3_u16x2(a, b, 0xFFFFFFFFu);
+  return (((d & 0x7FFF7FFFu) + kM) | d) & 0x80008000u;
+}
+
+template <typename Cfg, bool EDGE, int PITCH>
+__device__ __forceinline__ void comb_tile_rows_u16(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
+                                                   int y_first, const uint32_t* __restrict__ th_rows,
+                                                   uint32_t kM, uint32_t thS_bits, uint32_t thL_bits,
+                                                   uint32_t& oS, uint32_t& oL, uint32_t& oM) {
+  constexpr int R = Cfg::R;
+  const float thS = __uint_as_float(thS_bits), thL = __uint_as_float(thL_bits);
+  float fS[2] = { 0.0f, 0.0f }, fL[2] = { 0.0f, 0.0f };
+  uint32_t accM[2] = { 0u, 0u };
+  uint2 raw_c = *reinterpret_cast<const uint2*>(cur + 2 * PITCH), raw_n = *reinterpret_cast<const uint2*>(cur + 3 * PITCH);
+  F4 h0 = u16x4_to_float(*reinterpret_cast<const uint2*>(cur));
+  F4 h1 = u16x4_to_float(*reinterpret_cast<const uint2*>(cur + PITCH));
+  F4 h2 = u16x4_to_float(raw_c);
+  F4 h3 = u16x4_to_float(raw_n);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const uint2 raw_nn = *reinterpret_cast<const uint2*>(cur + (j + 4) * PITCH);
+    const F4 h4 = u16x4_to_float(raw_nn);
+    const uint2 pv = *reinterpret_cast<const uint2*>(prev + (j + 2) * PITCH);
+    const int f = j & 1;
+    float tS = thS, tL = thL;
+    if (EDGE) { tS = __uint_as_float(th_rows[j]); tL = __uint_as_float(th_rows[R + j]); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float t = h0.v[q] + h4.v[q];
+      t = __fmaf_rn(4.0f, h2.v[q], t);                      // exact: all operands are integers below 2^24
+      const float u = h1.v[q] + h3.v[q];
+      const float r = fabsf(__fmaf_rn(-3.0f, u, t));
+      fS[f] += (r >= tS) ? 1.0f : 0.0f;
+      fL[f] += (r >= tL) ? 1.0f : 0.0f;
+    }
+    accM[f] = __dp4a(halves_ge(raw_c.x, pv.x, kM), 0x01010101u, accM[f]);
+    accM[f] = __dp4a(halves_ge(raw_c.y, pv.y, kM), 0x01010101u, accM[f]);
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4; raw_c = raw_n; raw_n = raw_nn;
+  }
+  const int flip = y_first & 1;
+  const uint32_t s0 = (uint32_t)fS[0], s1 = (uint32_t)fS[1], l0 = (uint32_t)fL[0], l1 = (uint32_t)fL[1];
+  const uint32_t m0 = accM[0] >> 7, m1 = accM[1] >> 7;
+  oS = flip ? (s1 | (s0 << 16)) : (s0 | (s1 << 16));
+  oL = flip ? (l1 | (l0 << 16)) : (l0 | (l1 << 16));
+  oM = flip ? (m1 | (m0 << 16)) : (m0 | (m1 << 16));
+}
+
+template <typename Cfg, int BPS>
+__global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_constant__ CombArgs a) {
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte aligned ring base; pointer arithmetic stays on the __shared__ array so loads compile to LDS
@@ -209,7 +273,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
     const CUtensorMap* map = &a.map[merged ? 0 : pl];
     const int lt = seg.tile - P.tile0;
     const int ty = lt / P.tilesX, tx = lt - ty * P.tilesX;
-    const int x0 = tx * kCombTW, y0 = ty * Cfg::TH;
+    const int x0 = tx * (kCombTW / BPS), y0 = ty * Cfg::TH;      // TMA coordinates are in samples
     const int nf = seg.fend - seg.fbegin;
     const int nloads = nf + 1;                       // L_0 = previous frame, L_k = frame fbegin+k-1
     const int fprev = seg.fbegin > 0 ? seg.fbegin - 1 : seg.fbegin;
@@ -237,8 +301,9 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
       for (int i = tid; i < Cfg::RUNS * Cfg::R; i += Cfg::THREADS) {
         const int y = y0 + i;
         const bool ok = y >= 2 && y < P.H - 2;
-        th_tab[i / Cfg::R][0][i % Cfg::R] = ok ? P.thS : 0x7C007C00u;
-        th_tab[i / Cfg::R][1][i % Cfg::R] = ok ? P.thL : 0x7C007C00u;
+        const uint32_t inf = BPS == 1 ? 0x7C007C00u : 0x7F800000u;     // +inf as fp16x2 / fp32
+        th_tab[i / Cfg::R][0][i % Cfg::R] = ok ? P.thS : inf;
+        th_tab[i / Cfg::R][1][i % Cfg::R] = ok ? P.thL : inf;
       }
       __syncthreads();
     }
@@ -252,15 +317,19 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_u8_kernel(const __grid_cons
         const uint8_t* cur = tiles + st * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
         const uint8_t* prv = tiles + stp * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
         if (!edge) {
-          comb_tile_rows<Cfg, false, kCombTW>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
+          if (BPS == 1) comb_tile_rows<Cfg, false, kCombTW>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
+          else comb_tile_rows_u16<Cfg, false, kCombTW>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
         } else if (rows_live) {
-          comb_tile_rows<Cfg, true, kCombTW>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+          if (BPS == 1) comb_tile_rows<Cfg, true, kCombTW>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+          else comb_tile_rows_u16<Cfg, true, kCombTW>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
         }
       } else if (rows_live) {                        // half-width sub-tiles: row pitch 64 bytes
         constexpr int HP = kCombTW / 2, HTPR = HP / Cfg::STRIP;
         const int off = (strip / HTPR) * (Cfg::STAGE_BYTES / 2) + (run * Cfg::R) * HP + (strip % HTPR) * Cfg::STRIP;
-        comb_tile_rows<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off, y_first,
-                                      &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+        if (BPS == 1) comb_tile_rows<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off, y_first,
+                                                    &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+        else comb_tile_rows_u16<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off, y_first,
+                                               &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
       }
       vS = __reduce_add_sync(0xFFFFFFFFu, vS);
       vL = __reduce_add_sync(0xFFFFFFFFu, vL);

@@ -297,24 +297,44 @@ def test_scan_frames_unaligned_pitch_fallback(ctx, oracle):
     assert np.array_equal(got, po.or_comb_clip(Y, U, V, ab.default_comb_params().as_list()))
 
 
-def test_comb_16bit_generic_kernel(ctx, oracle):
-    """YUV420P10 clips: the integer spec on u16 samples (generic kernel), incl. range calls with a halo frame."""
+def test_comb_16bit(ctx, oracle, monkeypatch):
+    """YUV420P10 clips: the integer spec on u16 samples -- streaming (TMA, fp32 stencil) kernel incl. the merged U|V
+    remainder tile and range calls with a halo frame, and the generic kernel on the same data."""
     po = oracle
-    w, h, n = 224, 136, 7
-    f8 = synth.make_frames(2, n, w, h, device="cuda", mode="telecine")
-    f16 = (f8.to(torch.int32) * 4 + (f8.to(torch.int32) & 3)).to(torch.int16).contiguous()
-    clip = ab.yv12_clip(f16, w, h, n, True, bits=10)
     prm = ab.default_comb_params()
     prm.th_move_y, prm.th_shima_y, prm.th_lshima_y = 80, 48, 3000
     prm.th_move_c, prm.th_shima_c, prm.th_lshima_c = 200, 64, 144
+    for (w, h, n) in ((224, 136, 7), (320, 150, 5)):
+        f8 = synth.make_frames(2, n, w, h, device="cuda", mode="telecine")
+        f16 = (f8.to(torch.int32) * 4 + (f8.to(torch.int32) & 3)).to(torch.int16).contiguous()
+        clip = ab.yv12_clip(f16, w, h, n, True, bits=10)
+        got = ctx.comb_frames(clip, prm).cpu().numpy()
+        a16 = f16.cpu().numpy().view(np.uint16)
+        ysz, csz = w * h, (w // 2) * (h // 2)
+        Y = a16[:, :ysz].reshape(n, h, w); U = a16[:, ysz:ysz + csz].reshape(n, h // 2, w // 2); V = a16[:, ysz + csz:].reshape(n, h // 2, w // 2)
+        ref = po.or_comb_clip(Y, U, V, prm.as_list())
+        assert np.array_equal(got, ref) and ref[:, 1].sum() > 0, (w, h)
+        part = np.concatenate([ctx.comb_frames(clip, prm, 0, 3).cpu().numpy(), ctx.comb_frames(clip, prm, 3, n - 3).cpu().numpy()])
+        assert np.array_equal(part, ref)
+        monkeypatch.setenv("AMTK_COMB_GENERIC", "1")
+        g = ab.Context(0, torch.cuda.current_stream().cuda_stream)
+        monkeypatch.delenv("AMTK_COMB_GENERIC")
+        try:
+            assert np.array_equal(g.comb_frames(clip, prm).cpu().numpy(), ref)
+        finally:
+            g.close()
+            ab.Context(0, torch.cuda.current_stream().cuda_stream).close()      # restores the default knobs
+    # full-range 16-bit samples and the largest move threshold
+    w, h, n = 256, 136, 3
+    rnd = torch.randint(0, 65536, (n, w * h * 3 // 2), device="cuda", dtype=torch.int32).to(torch.int16).contiguous()
+    clip = ab.yv12_clip(rnd, w, h, n, True, bits=16)
+    prm.th_move_y, prm.th_move_c, prm.th_shima_y, prm.th_lshima_y = 32768, 1, 100000, 300000
     got = ctx.comb_frames(clip, prm).cpu().numpy()
-    a16 = f16.cpu().numpy().view(np.uint16)
+    a16 = rnd.cpu().numpy().view(np.uint16)
     ysz, csz = w * h, (w // 2) * (h // 2)
-    Y = a16[:, :ysz].reshape(n, h, w); U = a16[:, ysz:ysz + csz].reshape(n, h // 2, w // 2); V = a16[:, ysz + csz:].reshape(n, h // 2, w // 2)
-    ref = po.or_comb_clip(Y, U, V, prm.as_list())
-    assert np.array_equal(got, ref) and ref[:, 1].sum() > 0
-    part = np.concatenate([ctx.comb_frames(clip, prm, 0, 3).cpu().numpy(), ctx.comb_frames(clip, prm, 3, 4).cpu().numpy()])
-    assert np.array_equal(part, ref)
+    ref = po.or_comb_clip(a16[:, :ysz].reshape(n, h, w), a16[:, ysz:ysz + csz].reshape(n, h // 2, w // 2),
+                          a16[:, ysz + csz:].reshape(n, h // 2, w // 2), prm.as_list())
+    assert np.array_equal(got, ref)
 
 
 def test_scan_logo_pipeline(ctx, oracle, tmp_path):

@@ -58,6 +58,12 @@ print("AMTAnalyzeLogo (33 evals/frame): %.3f ms per %d frames -> %.0f frames/s" 
 fades = np.tile(np.array([[0.7, 0.7]], np.float32), (n, 1))
 ms = timed(lambda: ctx.erase_logo(clip, raw, fades))
 print("AMTEraseLogo in place: %.3f ms per %d frames -> %.0f frames/s" % (ms, n, n / ms * 1e3))
+# YUV420P10 through the streaming 16-bit kernel
+t16 = (t[:600].to(torch.int32) * 4 + 1).to(torch.int16).contiguous()
+clip16 = ab.yv12_clip(t16, w, h, 600, True, bits=10)
+ms = timed(lambda: ctx.comb_frames(clip16), reps=3)
+print("comb YUV420P10 1920x1080 x600 (streaming u16 kernel): %.3f ms -> %.0f frames/s  %.0f GB/s algorithmic" % (ms, 600 / ms * 1e3, 600 * w * h * 3.0 / ms / 1e6))
+del t16, clip16
 os.environ["AMTK_COMB_GENERIC"] = "1"
 ctx2 = ab.Context(0, torch.cuda.current_stream().cuda_stream)
 ms = timed(lambda: ctx2.comb_frames(clip), reps=2)
