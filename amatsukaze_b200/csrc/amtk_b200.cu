@@ -17,6 +17,7 @@ extern "C" { static int logo_ensure_device(const amtk_logo* cl, amtk_ctx* ctx, b
 namespace amtk {
 
 static thread_local std::string g_error;
+static int g_eval_waves = 1;          // logo_scores_kernel: CTAs per SM-slot to launch (env AMTK_EVAL_WAVES)
 void set_error(const std::string& msg) { g_error = msg; }
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -168,7 +169,8 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     int pxt = 3, slices = slices3;
     if (count <= kEvalThreads) { pxt = 1; slices = 1; }
     else if (count <= kEvalThreads * 2) { pxt = 2; slices = 1; }
-    const int lanes = std::max(1, std::min(n, (ctx->sm_count * 2) / slices));
+    // one CTA per SM (the kernel needs the whole register file): a single wave, so the tap tables are loaded once per SM
+    const int lanes = std::max(1, std::min(n, (ctx->sm_count * g_eval_waves) / slices));
     dim3 grid(slices, lanes);
     const bool u16 = clip->bytes_per_sample == 2;
 #define AMTK_LAUNCH_SCORES(T, P)                                                                              \
@@ -469,6 +471,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_GENERIC")) g_comb_force_generic = atoi(e);
   if (const char* e = getenv("AMTK_COMB_MERGE_UV")) g_comb_merge_uv = atoi(e);
   if (const char* e = getenv("AMTK_COMB_PART")) g_comb_part = atoi(e);
+  if (const char* e = getenv("AMTK_EVAL_WAVES")) g_eval_waves = std::max(1, atoi(e));
   if (const char* e = getenv("AMTK_COMB_L2")) g_comb_l2 = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }

@@ -281,7 +281,7 @@ def main():
     sampler.stop_flag = True
     peak, peak_src = measured_peak_gbs()
     if rank == 0:
-        # roofline of the dominant kernel (comb_u8_kernel): algorithmic bytes = one read of every frame byte
+        # roofline of the dominant kernel (comb_tma_kernel, 8-bit instantiation): algorithmic bytes = one read of every frame byte
         alg_bytes = CLIP_FRAMES * FRAME_BYTES
         avg_ms = comb_ms / max(comb_n, 1)
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
@@ -318,7 +318,7 @@ def main():
             "clocks": sampler.summary(),
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "comb_u8_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "comb_tma_kernel<CombCfg<17,8,3,0,8>,1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": int(comb_n),
                          "share_of_step": (comb_ms / max(elapsed_ms, 1e-9))},
