@@ -19,7 +19,7 @@ for n0 in range(0, frames, 20):
 clip = ab.yv12_clip(clip_t, W, H, frames, True)
 prm = ab.default_comb_params()
 ref = None
-combos = [(8, 3, 0, 0, 128, 0), (8, 2, 0, 0, 128, 0), (8, 4, 0, 0, 128, 0), (8, 2, 4, 0, 128, 0)]
+combos = [(8, 3, 0, 0, 128, 0), (8, 2, 0, 0, 128, 0), (8, 4, 0, 0, 128, 0), (8, 3, 0, 1, 128, 0), (8, 3, 3, 0, 128, 0), (8, 3, 0, 0, 0, 0)]
 if len(sys.argv) > 1:
     combos = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
 for strip, stages, ctas, acc, l2, R in combos:
