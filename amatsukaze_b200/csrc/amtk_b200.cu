@@ -17,6 +17,7 @@ extern "C" { static int logo_ensure_device(const amtk_logo* cl, amtk_ctx* ctx, b
 namespace amtk {
 
 static thread_local std::string g_error;
+static constexpr size_t kEvalSmemLimit = 226 * 1024;     // dynamic shared memory we ask for at most (227 KB per CTA on sm_100)
 static int g_eval_waves = 1;          // logo_scores_kernel: CTAs per SM-slot to launch (env AMTK_EVAL_WAVES)
 void set_error(const std::string& msg) { g_error = msg; }
 bool cuda_ok(cudaError_t e, const char* what) {
@@ -135,8 +136,12 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   const long long plane_rows = ((long long)clip->pitch_y * clip->height) / pitch_bytes;     // rows as addressed with pitch_elems
   const bool tma_ok = ctx->encode_tiled && box_w <= 256 && sp.roi_h <= 256 && (pitch_bytes & 15) == 0 &&
                       (clip->frame_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(win.dev_base) & 15) == 0;
-  const size_t smem = logo_scores_smem_bytes(sp.roi_w * sp.roi_h, hl.w * hl.h, box_w * sp.roi_h * bps);
-  if (smem > 200 * 1024) AMTK_FAIL("logo too large for the shared-memory evaluation path");
+  // shared-memory plan: everything for logos up to ~100x100, A/B through L1 up to ~16k px, one fade per pass beyond
+  int ab_smem = 1, pair_fades = 1;
+  size_t smem = logo_scores_smem_bytes(sp.roi_w * sp.roi_h, hl.w * hl.h, box_w * sp.roi_h * bps, ab_smem, pair_fades);
+  if (smem > kEvalSmemLimit) { ab_smem = 0; smem = logo_scores_smem_bytes(sp.roi_w * sp.roi_h, hl.w * hl.h, box_w * sp.roi_h * bps, ab_smem, pair_fades); }
+  if (smem > kEvalSmemLimit) { pair_fades = 0; smem = logo_scores_smem_bytes(sp.roi_w * sp.roi_h, hl.w * hl.h, box_w * sp.roi_h * bps, ab_smem, pair_fades); }
+  if (smem > kEvalSmemLimit) AMTK_FAIL("logo too large for the shared-memory evaluation path (more than ~24k pixels)");
   CUtensorMap roi_map;
   memset(&roi_map, 0, sizeof(roi_map));
   if (tma_ok) {
@@ -165,6 +170,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     for (int i = 0; i < sp.nfades; ++i) job.fades[i] = sp.fades[i];
     job.scores = reinterpret_cast<float*>(ctx->scratch);
     job.use_tma = tma_ok ? 1 : 0; job.roi_box_w = box_w; job.roi_box_x = box_x; job.roi_map = roi_map;
+    job.ab_smem = ab_smem; job.pair_fades = pair_fades;
     const int slices3 = (count + kEvalThreads * 3 - 1) / (kEvalThreads * 3);
     int pxt = 3, slices = slices3;
     if (count <= kEvalThreads) { pxt = 1; slices = 1; }

@@ -41,6 +41,8 @@ struct EvalJob {
   int use_tma;               // 1: the ROI is fetched by TMA through roi_map (box roi_box_w x roi_h x 1 elements)
   int roi_box_w;             // row pitch of the staged raw ROI in ELEMENTS (multiple of 16 bytes)
   int roi_box_x;             // x of the box in the frame: imgx rounded DOWN to 16 bytes (TMA faults on unaligned starts)
+  int ab_smem;               // 1: logo planes A,B are staged in shared memory; 0: read through L1 (large logos)
+  int pair_fades;            // 1: two fade levels per pass (needs a second work image in shared memory)
   CUtensorMap roi_map;       // 3-D (x, y, frame) view of the Y plane as addressed with `pitch`
 };
 
@@ -49,8 +51,9 @@ struct EvalJob {
 //   src[roi_n]         the frame's ROI as float (DeintY or CopyY)
 //   work[npx + 8] x2   logo-removed images of the current PAIR of fade levels
 //   raw[2][box_w*roi_h] pixel_t: double-buffered ROI samples, filled by TMA one frame ahead (128-byte aligned)
-__host__ __device__ inline size_t logo_scores_smem_bytes(int roi_n, int npx, int raw_bytes_one) {
-  return ((size_t)2 * ((npx + 3) & ~3) + ((roi_n + 3) & ~3) + 2 * (((size_t)npx + 8 + 3) & ~(size_t)3)) * sizeof(float) +
+__host__ __device__ inline size_t logo_scores_smem_bytes(int roi_n, int npx, int raw_bytes_one, int ab_smem, int pair_fades) {
+  return ((size_t)(ab_smem ? 2 : 0) * ((npx + 3) & ~3) + ((roi_n + 3) & ~3) +
+          (size_t)(pair_fades ? 2 : 1) * (((size_t)npx + 8 + 3) & ~(size_t)3)) * sizeof(float) +
          128 + 2 * (((size_t)raw_bytes_one + 127) & ~(size_t)127);
 }
 
@@ -62,19 +65,20 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __gr
   const LogoDev& lg = job.logo;
   const int w = lg.w, npx = lg.w * lg.h;
   const int roi_n = job.roi_w * job.roi_h;
-  float* sA = smem_f;
-  float* sB = sA + ((npx + 3) & ~3);
-  float* src = sB + ((npx + 3) & ~3);
+  float* src = smem_f + (job.ab_smem ? 2 * ((npx + 3) & ~3) : 0);
+  const float* sA = job.ab_smem ? smem_f : lg.A;                         // large logos read A,B through L1 instead
+  const float* sB = job.ab_smem ? smem_f + ((npx + 3) & ~3) : lg.B;
   float* work = src + ((roi_n + 3) & ~3);
-  float* work2 = work + ((npx + 8 + 3) & ~3);                            // second fade level of a pair
-  uint8_t* raw_base = reinterpret_cast<uint8_t*>(work2 + ((npx + 8 + 3) & ~3));
+  float* work2 = work + ((npx + 8 + 3) & ~3);                            // second fade level of a pair (pair_fades only)
+  uint8_t* raw_base = reinterpret_cast<uint8_t*>(work + (size_t)(job.pair_fades ? 2 : 1) * ((npx + 8 + 3) & ~3));
   raw_base += (128u - (smem_u32(raw_base) & 127u)) & 127u;
   const int raw_pitch = job.roi_box_w;                                   // elements per staged ROI row
   const uint32_t raw_bytes = (uint32_t)raw_pitch * job.roi_h * sizeof(pixel_t);
   const uint32_t raw_stride = (raw_bytes + 127u) & ~127u;
 
   // ---- one-time: logo planes to smem, adopt feature pixels, pull their taps into registers ----
-  for (int i = tid; i < npx; i += kEvalThreads) { sA[i] = lg.A[i]; sB[i] = lg.B[i]; }
+  if (job.ab_smem)
+    for (int i = tid; i < npx; i += kEvalThreads) { smem_f[i] = lg.A[i]; smem_f[((npx + 3) & ~3) + i] = lg.B[i]; }
   float taps[PXT][25];
   int pxy[PXT];
   int cidx[PXT];
@@ -150,8 +154,9 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __gr
 
     // Fade levels are processed in PAIRS: both logo-removed images are built in one phase and every thread then scores
     // its pixels on both (6 independent dependency chains instead of 3, half as many block barriers per frame).
-    for (int fi = 0; fi < job.nfades; fi += 2) {
-      const int nf2 = min(2, job.nfades - fi);
+    const int fstep = job.pair_fades ? 2 : 1;
+    for (int fi = 0; fi < job.nfades; fi += fstep) {
+      const int nf2 = min(fstep, job.nfades - fi);
       const float fade0 = job.fades[fi], fade1 = job.fades[fi + nf2 - 1];
       const float omf0 = AMTK_FSUB(1.0f, fade0), omf1 = AMTK_FSUB(1.0f, fade1);
       // ---- logo removal at these fade levels (LogoScan.hpp:241-251) ----

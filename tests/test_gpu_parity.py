@@ -424,3 +424,32 @@ def test_weave_frames_matches_mergefield(ctx):
     assert torch.equal(dst, ref)
     with pytest.raises(ab.AmtkError, match="index outside"):
         ctx.weave_frames(ab.yv12_clip(src8, w, h, n, True), ab.yv12_clip(dst, w, h, n, True), top, bot + 1)
+
+
+def test_logo_sizes_small_large_multislice(ctx, oracle):
+    """Logo geometry sweep: PXT=1 (few features), several pixel slices (> 1536 features), A/B-through-L1 and
+    one-fade-per-pass shared-memory plans for large logos; also the analyze path on a wide flat logo."""
+    po = oracle
+    W2, H2 = 640, 288
+    n = 3
+    fr = synth.make_frames(11, n, W2, H2, device="cuda", mode="interlaced")
+    Y, _, _ = synth.split_planes(fr, W2, H2)
+    for (w, h, ratio, imgx, imgy) in ((32, 32, 0.35, 300, 100), (128, 96, 0.35, 410, 66), (200, 112, 0.2, 96, 120), (256, 90, 0.5, 320, 4)):
+        lg = synth.make_logo(w, h, seed=w)
+        p = ab.Logo.create(lg["data"], w, h, W2, H2, imgx, imgy)
+        o = po.OracleLogo.create(lg["data"], w, h, W2, H2, imgx, imgy)
+        pd, od = p.deint().create_mask(ratio), o.deint().create_mask(ratio)
+        assert pd.info().count == od.s.count
+        out = ctx.scan_frames(_clip(fr, W2, H2), [pd]).cpu().numpy()
+        ref = np.stack([od.scan_frame(Y[i]) for i in range(n)])
+        assert np.array_equal(_bits(out[:, 0]), _bits(ref)), (w, h, pd.info().count)
+        if h % 2 == 0 and h // 2 >= 5:
+            pt, pb = p.field(0).create_mask(ratio), p.field(1).create_mask(ratio)
+            ot, ob = o.field(0).create_mask(ratio), o.field(1).create_mask(ratio)
+            an = ctx.analyze_frames(_clip(fr, W2, H2), pd, pt, pb, nframes=2).cpu().numpy()
+            ra = np.stack([po.or_analyze_frame(od, ot, ob, Y[i]) for i in range(2)])
+            assert np.array_equal(_bits(an), _bits(ra)), (w, h)
+    huge = synth.make_logo(256, 128, seed=9)
+    ph = ab.Logo.create(huge["data"], 256, 128, W2, H2, 64, 32).deint().create_mask(0.1)
+    with pytest.raises(ab.AmtkError, match="too large"):
+        ctx.scan_frames(_clip(fr, W2, H2), [ph])
