@@ -66,10 +66,12 @@ AMTK_API int amtk_memcpy_d2h(amtk_ctx* ctx, void* dst_host, const void* src_devi
  * ------------------------------------------------------------------------------------------- */
 typedef struct amtk_clip {
   const void* base;        /* first byte of frame 0 (its Y plane)                                  */
-  int64_t frame_stride;    /* bytes from one frame to the next (multiple of 16)                    */
-  int64_t off_u, off_v;    /* byte offsets of the U and V planes inside a frame (multiples of 16)  */
+  int64_t frame_stride;    /* bytes from one frame to the next                                     */
+  int64_t off_u, off_v;    /* byte offsets of the U and V planes inside a frame                    */
   int32_t width, height;   /* luma size in pixels                                                  */
-  int32_t pitch_y, pitch_uv; /* bytes per row (multiples of 16)                                    */
+  int32_t pitch_y, pitch_uv; /* bytes per row.  When base, frame_stride, off_u/off_v and the pitches are  */
+                             /* all multiples of 16 bytes the TMA streaming kernels run; any other layout */
+                             /* takes slower plain-load kernels with identical results                    */
   int32_t log_uvx, log_uvy;  /* chroma subsampling shifts (1,1 for YV12 / YUV420P10)               */
   int32_t bytes_per_sample;  /* 1 (YV12) or 2 (YUV420P10/P12/P16, little endian)                   */
   int32_t bits_per_sample;   /* 8, 10, 12 or 16: maxv = (1<<bits)-1 (LogoScan.hpp:1130,1575)       */
@@ -137,8 +139,9 @@ AMTK_API int amtk_logo_eval_fades(amtk_ctx* ctx, const amtk_clip* clip, const am
 /* ---------------------------------------------------------------------------------------------
  * Field-difference / combing metric (the telecine pre-pass the reference drives through
  * AMTFilterSource::FilterPass/ReadAllFrames, FilteredSource.hpp:232-238,417-439,519-544, and computes in the
- * external KFM plugin).  Integer spec: DESIGN.md section 4.
+ * external KFM plugin).  Integer spec: DESIGN.md section 4; 8-bit and 16-bit (YUV420P10/12/16) samples.
  * counts int32[nframes][12] = [plane class Y,C][field top,bottom][move, shima, lshima].
+ * Thresholds: 8-bit th_move in [1,128], th_shima/th_lshima in [1,2047]; 16-bit th_move in [1,32768], others >= 1.
  * ------------------------------------------------------------------------------------------- */
 typedef struct amtk_comb_params {
   int32_t th_move_y, th_shima_y, th_lshima_y;   /* defaults 20, 12, 36 */
