@@ -54,6 +54,7 @@ SIGNATURES = [
     ("amtk_ctx_launch_count", C.c_int64, [V]),
     ("amtk_ctx_set_kernel_timing", C.c_int, [V, C.c_int]),
     ("amtk_ctx_get_kernel_timing", C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    ("amtk_probe_read_ms", C.c_int, [V, V, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     ("amtk_host_alloc", C.c_int, [C.c_size_t, VP]),
     ("amtk_host_free", None, [V]),
     ("amtk_device_alloc", C.c_int, [V, C.c_size_t, VP]),
@@ -175,6 +176,13 @@ class Context:
 
     def set_kernel_timing(self, enable):
         check(self.L.amtk_ctx_set_kernel_timing(self.h, int(enable)))
+
+    def probe_read_gbs(self, tensor, reps=3):
+        """GB/s of a do-nothing streaming read of `tensor` (device) -- the read-only HBM ceiling on this GPU."""
+        ms = C.c_double()
+        nbytes = tensor.numel() * tensor.element_size()
+        check(self.L.amtk_probe_read_ms(self.h, _ptr(tensor), nbytes, reps, C.byref(ms)))
+        return nbytes / (ms.value * 1e-3) / 1e9
 
     def kernel_timing(self, reset=True):
         """(total ms, launches) of the comb kernel since the last reset, from CUDA events on the launch stream."""

@@ -529,6 +529,27 @@ int amtk_ctx_get_kernel_timing(amtk_ctx* c, double* ms_total, int64_t* launches,
   return 1;
 }
 
+int amtk_probe_read_ms(amtk_ctx* c, const void* ptr, size_t bytes, int reps, double* ms_out) {
+  if (!c || !ptr || !ms_out || reps < 1) AMTK_FAIL("amtk_probe_read_ms: bad argument");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) AMTK_FAIL("amtk_probe_read_ms: pointer must be 16-byte aligned");
+  DevSelect ds(c); if (!ds.ok) return 0;
+  if (!ensure(&c->small, &c->small_bytes, 256)) return 0;
+  cudaEvent_t e0, e1;
+  AMTK_CUDA(cudaEventCreate(&e0)); AMTK_CUDA(cudaEventCreate(&e1));
+  const int grid = c->sm_count * 8;
+  unsigned* sink = reinterpret_cast<unsigned*>(c->small);
+  read_probe_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(ptr), bytes / 16, sink);
+  AMTK_CUDA(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < reps; ++i) read_probe_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(ptr), bytes / 16, sink);
+  AMTK_CUDA(cudaEventRecord(e1, c->stream));
+  AMTK_CUDA(cudaEventSynchronize(e1));
+  float ms = 0; AMTK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  AMTK_CUDA(cudaGetLastError());
+  *ms_out = ms / reps;
+  return 1;
+}
+
 int amtk_host_alloc(size_t bytes, void** out) {
   if (!out) AMTK_FAIL("amtk_host_alloc: out is null");
   AMTK_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));

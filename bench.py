@@ -279,21 +279,8 @@ def main():
         del host
 
     # read-only ceiling on this GPU: a plain streaming reduction over the same 5.6 GB clip
-    read_ceiling = None
-    try:
-        v32 = clip_t.view(-1)[: (clip_t.numel() // 4) * 4].view(torch.int32)
-        with torch.cuda.stream(stream):
-            for _ in range(2):
-                v32.sum()
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record(stream)
-            for _ in range(3):
-                v32.sum()
-            r1.record(stream)
-            stream.synchronize()
-        read_ceiling = v32.numel() * 4 * 3 / (r0.elapsed_time(r1) * 1e-3) / 1e9
-    except Exception:
-        read_ceiling = None
+    with torch.cuda.stream(stream):
+        read_ceiling = ctx.probe_read_gbs(clip_t, reps=3)
 
     sampler.stop_flag = True
     peak, peak_src = measured_peak_gbs()

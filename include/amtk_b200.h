@@ -49,6 +49,11 @@ AMTK_API int64_t amtk_ctx_launch_count(const amtk_ctx* ctx);
 AMTK_API int amtk_ctx_set_kernel_timing(amtk_ctx* ctx, int enable);
 AMTK_API int amtk_ctx_get_kernel_timing(amtk_ctx* ctx, double* ms_total, int64_t* launches, int reset);
 
+/* Measurement helper: a trivial streaming read (uint4 loads, XOR-reduced) over [ptr, ptr+bytes) on the context's
+ * stream, timed with CUDA events; returns the average milliseconds of `reps` passes after one warm-up pass.
+ * bench.py reports bytes/ms as the read-only HBM ceiling next to the roofline numbers. */
+AMTK_API int amtk_probe_read_ms(amtk_ctx* ctx, const void* device_ptr, size_t bytes, int reps, double* ms_out);
+
 /* Pinned host memory for the host-buffer entry points (optional; pageable memory works, only slower). */
 AMTK_API int amtk_host_alloc(size_t bytes, void** out);
 AMTK_API void amtk_host_free(void* p);
