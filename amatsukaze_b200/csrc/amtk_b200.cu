@@ -18,7 +18,6 @@ namespace amtk {
 
 static thread_local std::string g_error;
 static constexpr size_t kEvalSmemLimit = 226 * 1024;     // dynamic shared memory we ask for at most (227 KB per CTA on sm_100)
-static int g_eval_waves = 1;          // logo_scores_kernel: CTAs per SM-slot to launch (env AMTK_EVAL_WAVES)
 void set_error(const std::string& msg) { g_error = msg; }
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -176,7 +175,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     if (count <= kEvalThreads) { pxt = 1; slices = 1; }
     else if (count <= kEvalThreads * 2) { pxt = 2; slices = 1; }
     // one CTA per SM (the kernel needs the whole register file): a single wave, so the tap tables are loaded once per SM
-    const int lanes = std::max(1, std::min(n, (ctx->sm_count * g_eval_waves) / slices));
+    const int lanes = std::max(1, std::min(n, (ctx->sm_count * ctx->knobs.eval_waves) / slices));
     dim3 grid(slices, lanes);
     const bool u16 = clip->bytes_per_sample == 2;
 #define AMTK_LAUNCH_SCORES(T, P)                                                                              \
@@ -252,8 +251,6 @@ static const CombVariant* comb_variants(int* n) {
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }
-static int g_comb_force_generic = 0, g_comb_merge_uv = 1, g_comb_part = -1;   // part: -1 auto, 0 equal-share, 1 lock-step
-static int g_comb_strip = 8, g_comb_stages = 3, g_comb_R = 0, g_comb_ctas_per_sm = 0, g_comb_acc = 0, g_comb_l2 = 128;   // tuning knobs (env AMTK_COMB_*)
 
 // rows per run: the R in {15,16,17} that wastes the fewest rows over luma + chroma (1080/540 -> 17, 720/360 -> 15)
 static int pick_comb_R(int hY, int hC) {
@@ -270,7 +267,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
                        const amtk_comb_params* prm, int* dcounts, int out_row0) {
   const bool tma_layout = !((clip->frame_stride & 15) || (clip->pitch_y & 15) || (clip->pitch_uv & 15) || (clip->off_u & 15) ||
                             (clip->off_v & 15) || (reinterpret_cast<uintptr_t>(win.dev_base) & 15));
-  if (!tma_layout || !ctx->encode_tiled || g_comb_force_generic) {
+  if (!tma_layout || !ctx->encode_tiled || ctx->knobs.comb_generic) {
     // generic kernel: any sample size / pitch (DESIGN.md 3.1 "fallback")
     CombGenericArgs g;
     g.base = win.dev_base; g.frame_stride = clip->frame_stride;
@@ -300,9 +297,9 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     return 1;
   }
   const int hY = clip->height, hC = clip->height >> clip->log_uvy;
-  const int R = g_comb_R ? g_comb_R : pick_comb_R(hY, hC);
+  const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_comb_R(hY, hC);
   int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
-  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == g_comb_strip && vars[i].stages == g_comb_stages && vars[i].acc == g_comb_acc) V = &vars[i];
+  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == ctx->knobs.comb_strip && vars[i].stages == ctx->knobs.comb_stages && vars[i].acc == ctx->knobs.comb_acc) V = &vars[i];
   if (!V) AMTK_FAIL("comb: no kernel variant for the requested AMTK_COMB_* settings");
   const int bps = clip->bytes_per_sample;
   if (bps == 2 && !V->kernel16) AMTK_FAIL("comb: the selected AMTK_COMB_* variant has no 16-bit kernel");
@@ -313,7 +310,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   // instead of two half-empty ones.
   const int wC = clip->width >> clip->log_uvx;
   const int rem = wC % twe;
-  const bool merge_uv = g_comb_merge_uv && rem > 0 && rem <= twe / 2 && (V->boxH * (kCombTW / 2)) % 128 == 0;
+  const bool merge_uv = ctx->knobs.comb_merge_uv && rem > 0 && rem <= twe / 2 && (V->boxH * (kCombTW / 2)) % 128 == 0;
   int tile0 = 0;
   for (int pl = 0; pl < 4; ++pl) {
     CombPlane& P = args.plane[pl];
@@ -342,8 +339,8 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     cuuint64_t gdim[3] = { (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)win.count };
     cuuint64_t gstr[2] = { (cuuint64_t)pitch, (cuuint64_t)clip->frame_stride };
     cuuint32_t estr[3] = { 1u, 1u, 1u };
-    const CUtensorMapL2promotion promo = g_comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : g_comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
-                                         g_comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    const CUtensorMapL2promotion promo = ctx->knobs.comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : ctx->knobs.comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                         ctx->knobs.comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     for (int half = 0; half < (pl && merge_uv ? 2 : 1); ++half) {
       cuuint32_t box[3] = { (cuuint32_t)(half ? twe / 2 : twe), (cuuint32_t)V->boxH, 1u };
       CUtensorMap* m = half ? &args.map_half[pl - 1] : &args.map[pl];
@@ -363,7 +360,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   AMTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
   AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, V->threads, V->smem));
   if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
-  if (g_comb_ctas_per_sm > 0) occ = std::min(occ, g_comb_ctas_per_sm);
+  if (ctx->knobs.comb_ctas > 0) occ = std::min(occ, ctx->knobs.comb_ctas);
   const long long total = (long long)ntiles * nf;
   int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, total);
   std::vector<CombSegment> segs;
@@ -371,7 +368,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   // frames at the same time and share halo rows / straddled 128-byte lines through L2.  Used when the plane pitch
   // makes tile rows straddle lines (pitch % 128 != 0 on luma) or when forced; costs a few idle CTA slots.
   const int chunks = std::max(1, std::min(nf, grid / std::max(1, ntiles)));
-  const bool lockstep = g_comb_part == 1 || (g_comb_part < 0 && (clip->pitch_y % 128) != 0 && chunks * ntiles * 10 >= grid * 9);
+  const bool lockstep = ctx->knobs.comb_part == 1 || (ctx->knobs.comb_part < 0 && (clip->pitch_y % 128) != 0 && chunks * ntiles * 10 >= grid * 9);
   if (lockstep) grid = chunks * ntiles;
   std::vector<int> seg_start((size_t)grid + 1, 0);
   if (lockstep) {
@@ -465,17 +462,17 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
     else cudaGetLastError();
   });
   c->encode_tiled = g_encode;
-  // tuning knobs for the comb kernel variant (defaults are the measured best)
-  if (const char* e = getenv("AMTK_COMB_STRIP")) g_comb_strip = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_STAGES")) g_comb_stages = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_R")) g_comb_R = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_CTAS")) g_comb_ctas_per_sm = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_ACC")) g_comb_acc = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_GENERIC")) g_comb_force_generic = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_MERGE_UV")) g_comb_merge_uv = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_PART")) g_comb_part = atoi(e);
-  if (const char* e = getenv("AMTK_EVAL_WAVES")) g_eval_waves = std::max(1, atoi(e));
-  if (const char* e = getenv("AMTK_COMB_L2")) g_comb_l2 = atoi(e);
+  // per-context tuning knobs (defaults are the measured best; env AMTK_* overrides them for tools/tune_comb.py)
+  if (const char* e = getenv("AMTK_COMB_STRIP")) c->knobs.comb_strip = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_STAGES")) c->knobs.comb_stages = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_R")) c->knobs.comb_R = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_CTAS")) c->knobs.comb_ctas = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_ACC")) c->knobs.comb_acc = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_GENERIC")) c->knobs.comb_generic = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_MERGE_UV")) c->knobs.comb_merge_uv = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_PART")) c->knobs.comb_part = atoi(e);
+  if (const char* e = getenv("AMTK_EVAL_WAVES")) c->knobs.eval_waves = std::max(1, atoi(e));
+  if (const char* e = getenv("AMTK_COMB_L2")) c->knobs.comb_l2 = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }
   *out = c;

@@ -59,6 +59,13 @@ struct amtk_ctx {
   void* dout = nullptr; size_t dout_bytes = 0;             // device-side outputs when the caller's are on the host
   void* dout2 = nullptr; size_t dout2_bytes = 0;
   amtk_encode_tiled_fn encode_tiled = nullptr;
+  struct Knobs {            // kernel-variant selection; read from AMTK_* environment variables at context creation
+    int eval_waves = 1;     // logo_scores_kernel CTAs per SM
+    int comb_generic = 0;   // 1: force the plain-load comb kernel
+    int comb_merge_uv = 1;  // U|V remainder columns share one tile
+    int comb_part = -1;     // partition: -1 auto, 0 equal-share, 1 lock-step
+    int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_acc = 0, comb_l2 = 128;
+  } knobs;
   // optional per-launch timing of the dominant (comb) kernel with CUDA events on the launching stream
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;   // recorded, not yet resolved
