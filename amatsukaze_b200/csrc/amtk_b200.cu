@@ -750,6 +750,7 @@ static int scan_frames_impl(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* con
 
 int amtk_logo_scan_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
                           int frame0, int nframes, int pitch_override, float* out, int out_on_device) {
+  if (ctx && nframes == 0) return 1;                                 // empty range: nothing to do
   if (!ctx || !logos || !out || nlogos < 1) AMTK_FAIL("amtk_logo_scan_frames: bad argument");
   if (!validate_clip(clip, false)) return 0;
   DevSelect ds(ctx); if (!ds.ok) return 0;
@@ -780,6 +781,7 @@ static int analyze_impl(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* d
 
 int amtk_logo_analyze_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* dl, const amtk_logo* ft, const amtk_logo* fb,
                              int frame0, int nframes, float* out, int out_on_device) {
+  if (ctx && nframes == 0) return 1;
   if (!ctx || !dl || !ft || !fb || !out) AMTK_FAIL("amtk_logo_analyze_frames: bad argument");
   if (!validate_clip(clip, false)) return 0;
   if (ft->host.w != dl->host.w || fb->host.w != dl->host.w || ft->host.h != dl->host.h / 2 || fb->host.h != dl->host.h / 2)
@@ -796,6 +798,7 @@ int amtk_logo_analyze_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_lo
 
 int amtk_logo_eval_fades(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* dl, const float* fades, int nfades,
                          int frame0, int nframes, float* out, int out_on_device) {
+  if (ctx && nframes == 0) return 1;
   if (!ctx || !dl || !fades || !out) AMTK_FAIL("amtk_logo_eval_fades: bad argument");
   if (nfades < 1 || nfades > kMaxFades) AMTK_FAIL("amtk_logo_eval_fades: 1..24 fade levels");
   if (!validate_clip(clip, false)) return 0;
@@ -823,6 +826,7 @@ void amtk_comb_default_params(amtk_comb_params* p) {
 
 int amtk_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_comb_params* prm, int frame0, int nframes,
                      int32_t* counts, int out_on_device) {
+  if (ctx && nframes == 0) return 1;
   if (!ctx || !prm || !counts) AMTK_FAIL("amtk_comb_frames: bad argument");
   if (!validate_clip(clip, true) || !comb_thresholds_ok(prm, clip->bytes_per_sample)) return 0;
   DevSelect ds(ctx); if (!ds.ok) return 0;
@@ -837,6 +841,7 @@ int amtk_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_comb_param
 
 int amtk_scan_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
                           const amtk_comb_params* prm, int frame0, int nframes, float* scores, int32_t* counts, int out_on_device) {
+  if (ctx && nframes == 0) return 1;
   if (!ctx || !prm || !counts || !scores || !logos || nlogos < 1) AMTK_FAIL("amtk_scan_comb_frames: bad argument");
   if (!validate_clip(clip, true) || !comb_thresholds_ok(prm, clip->bytes_per_sample)) return 0;
   DevSelect ds(ctx); if (!ds.ok) return 0;

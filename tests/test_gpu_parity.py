@@ -453,3 +453,28 @@ def test_logo_sizes_small_large_multislice(ctx, oracle):
     ph = ab.Logo.create(huge["data"], 256, 128, W2, H2, 64, 32).deint().create_mask(0.1)
     with pytest.raises(ab.AmtkError, match="too large"):
         ctx.scan_frames(_clip(fr, W2, H2), [ph])
+
+
+def test_empty_single_and_bad_ranges(ctx, oracle):
+    po = oracle
+    lg, P, O = _logos(po)
+    fr = synth.make_frames(77, 3, W, H, device="cuda", logo=lg, imgx=IMGX, imgy=IMGY)
+    clip = _clip(fr, W, H)
+    prm = ab.default_comb_params()
+    # empty range: succeeds, returns empty arrays
+    assert ctx.comb_frames(clip, prm, 1, 0).shape[0] == 0
+    assert ctx.scan_frames(clip, [P["deint"]], 2, 0).shape[0] == 0
+    # single frame in the middle: move compares with the real predecessor
+    one = ctx.comb_frames(clip, prm, 2, 1).cpu().numpy()
+    Y, U, V = synth.split_planes(fr, W, H)
+    assert np.array_equal(one[0], po.or_comb_frame((Y[2], U[2], V[2]), (Y[1], U[1], V[1]), prm.as_list()))
+    # a one-frame clip: prev(0) = itself -> no motion
+    c1 = _clip(fr[:1].contiguous(), W, H)
+    s, c = ctx.scan_comb_frames(c1, [P["deint"]], prm)
+    assert c.cpu().numpy()[0, [0, 3, 6, 9]].sum() == 0
+    assert np.array_equal(_bits(s.cpu().numpy()[0, 0]), _bits(O["deint"].scan_frame(Y[0])))
+    for (f0, n) in ((-1, 2), (2, 2), (0, 4)):
+        with pytest.raises(ab.AmtkError, match="frame range"):
+            ctx.comb_frames(clip, prm, f0, n)
+    with pytest.raises(ab.AmtkError, match="no mask"):
+        ctx.scan_frames(clip, [P["raw"].deint()])
