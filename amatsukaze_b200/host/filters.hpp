@@ -655,6 +655,73 @@ inline int WriteTelecineFiles(const std::vector<int32_t>& counts, int num_frames
   return film_cycles;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CMAnalyze (CMAnalyze.hpp:22-317) -- the logo-analysis half only: the constructor runs logoFrame() when logos are
+// configured and exposes getLogoPath().  chapter_exe / join_logo_scp subprocesses, Trim/zone parsing (:319-679) are
+// out of scope.  ConfigWrapper is reduced to the accessors logoFrame() reads.
+// ---------------------------------------------------------------------------------------------------------------
+struct ConfigWrapper {
+  std::vector<tstring> logoPath, eraseLogoPath;          // --logo / --erase-logo (AmatsukazeCLI.hpp:358-366)
+  bool looseLogoDetection = false;                       // --loose-logo-detection (:370)
+  tstring tmpDir = ".";
+  const std::vector<tstring>& getLogoPath() const { return logoPath; }
+  const std::vector<tstring>& getEraseLogoPath() const { return eraseLogoPath; }
+  bool isLooseLogoDetection() const { return looseLogoDetection; }
+  tstring getTmpAMTSourcePath(int v) const { return tmpDir + "/amts" + std::to_string(v) + ".dat"; }            // TranscodeSetting.hpp:926-928
+  tstring getTmpLogoFramePath(int v, int logoIndex = -1) const {                                               // :934-939
+    return tmpDir + "/logof" + std::to_string(v) + (logoIndex == -1 ? std::string() : "-" + std::to_string(logoIndex)) + ".txt";
+  }
+};
+
+struct AviSynthException : std::runtime_error { using std::runtime_error::runtime_error; };
+
+class CMAnalyze {
+public:
+  // env must have the plugin registered (AvisynthPluginInit3) and an amtk context bound; the reference creates its
+  // own script environment and loads itself as a plugin (:275-280) -- on the B200 build the caller owns the device.
+  CMAnalyze(AMTContext& ctx, const ConfigWrapper& setting, int videoFileIndex, int /*numFrames*/, IScriptEnvironment2* env)
+      : ctx(ctx), setting_(setting) {
+    if (setting_.getLogoPath().size() > 0 || setting_.getEraseLogoPath().size() > 0) {                        // :34
+      ctx.info("[logo analysis]");
+      logoFrame(videoFileIndex, env);
+      if (logopath.size() > 0) ctx.infoF("matched logo: %s", logopath.c_str());
+    }
+  }
+  const tstring& getLogoPath() const { return logopath; }
+  float getLogoRatio() const { return logoRatio; }
+private:
+  AMTContext& ctx;
+  const ConfigWrapper& setting_;
+  tstring logopath;
+  float logoRatio = 0.0f;
+
+  void logoFrame(int videoFileIndex, IScriptEnvironment2* env) {                                              // :273-317
+    try {
+      PClip clip = env->Invoke("AMTSource", AVSValue(std::vector<AVSValue>{ AVSValue(setting_.getTmpAMTSourcePath(videoFileIndex)) })).AsClip();
+      const VideoInfo vi = clip->GetVideoInfo();
+      const int duration = (int)((int64_t)vi.num_frames * vi.fps_denominator / vi.fps_numerator);
+      const auto& logoPath = setting_.getLogoPath();
+      const auto& eraseLogoPath = setting_.getEraseLogoPath();
+      std::vector<tstring> allLogoPath = logoPath;
+      allLogoPath.insert(allLogoPath.end(), eraseLogoPath.begin(), eraseLogoPath.end());
+      logo::LogoFrame logof(ctx, allLogoPath, 0.35f);
+      logof.scanFrames(clip, env);                       // ONE batched device pass for all logos
+      if (logoPath.size() > 0) {
+        logof.selectLogo((int)logoPath.size());
+        logof.writeResult(setting_.getTmpLogoFramePath(videoFileIndex));
+        logoRatio = logof.getLogoRatio();
+        const float threshold = setting_.isLooseLogoDetection() ? 0.03f : (duration <= 60 * 7) ? 0.03f : 0.1f;
+        if (logoRatio < threshold) ctx.info("no logo matched in this section");
+        else logopath = setting_.getLogoPath()[logof.getBestLogo()];
+      }
+      for (int i = 0; i < (int)eraseLogoPath.size(); ++i)
+        logof.writeResult(setting_.getTmpLogoFramePath(videoFileIndex, i), (int)logoPath.size() + i);
+    } catch (const AvisynthError& avserror) {
+      throw AviSynthException(avserror.msg);                                                                  // :314-316
+    }
+  }
+};
+
 // Registration with the reference's names and argument specs (Amatsukaze.cpp:43-66).
 extern "C" inline const char* __stdcall AvisynthPluginInit3(IScriptEnvironment* env, const AVS_Linkage* const) {
   env->AddFunction("AMTSource", "s[filter]s[outqp]b", av::CreateAMTSource, 0);

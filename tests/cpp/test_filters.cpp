@@ -84,6 +84,22 @@ int main(int argc, char** argv) {
         rc = 1;
       } catch (const AvisynthError& e) { printf("expected error: %s\n", e.msg.c_str()); }
     }
+    // ---- CMAnalyze ctor -> logoFrame (CMAnalyze.hpp:25-47,273-317): one match logo + the same logo as an erase logo ----
+    {
+      ConfigWrapper setting;
+      setting.tmpDir = out;
+      setting.logoPath = { out + "/does-not-exist.lgd", logoPath };
+      setting.eraseLogoPath = { logoPath };
+      { FILE* a = fopen(clipPath.c_str(), "rb"); FILE* b = fopen(setting.getTmpAMTSourcePath(0).c_str(), "wb");
+        std::vector<char> buf(1 << 20); size_t n;
+        while ((n = fread(buf.data(), 1, buf.size(), a)) > 0) fwrite(buf.data(), 1, n, b);
+        fclose(a); fclose(b); }
+      CMAnalyze cma(ctx, setting, 0, vi.num_frames, env);
+      printf("cmanalyze: logopath=%s ratio=%.6f\n", cma.getLogoPath().c_str(), cma.getLogoRatio());
+      ConfigWrapper none; none.tmpDir = out;
+      CMAnalyze idle(ctx, none, 0, vi.num_frames, env);          // no logos configured: nothing runs, empty path
+      printf("cmanalyze idle: '%s'\n", idle.getLogoPath().c_str());
+    }
     // ---- error behaviour ----
     try {
       env->Invoke("AMTAnalyzeLogo", AVSValue(std::vector<AVSValue>{ AVSValue(clip), AVSValue(out + "/nope.lgd"), AVSValue(35) }));

@@ -63,6 +63,17 @@ def test_logoframe_scan_select_write(run):
         assert txt == open(rp).read() and len(txt.splitlines()) >= 2
 
 
+def test_cmanalyze_logoframe_entry(run):
+    """CMAnalyze ctor -> logoFrame (CMAnalyze.hpp:25-47,273-317): picks the readable logo among the --logo list, writes
+    logof0.txt for it and logof0-0.txt for the erase logo (TranscodeSetting.hpp:934-939)."""
+    out = run["out"]
+    assert ("cmanalyze: logopath=%s " % (out / "logo.lgd")) in run["stdout"]
+    assert "cmanalyze idle: ''" in run["stdout"]
+    txt = open(out / "logof.txt").read()
+    assert open(out / "logof0.txt").read() == txt           # same scores, same selection as the direct LogoFrame run
+    assert open(out / "logof0-0.txt").read() == txt
+
+
 def test_logoframe_write_result_matches_reference_on_many_patterns(run, tmp_path):
     """selectLogo/writeResult are pure host code: exercise them on synthetic score tracks against the reference's own
     implementation (oracle/_ref, LogoScan.hpp:1645-1827 compiled verbatim)."""
