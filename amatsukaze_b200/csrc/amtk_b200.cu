@@ -366,9 +366,11 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   std::vector<CombSegment> segs;
   // "lock-step" partition: every tile is cut into the same C frame ranges, so neighbouring tiles stream the same
   // frames at the same time and share halo rows / straddled 128-byte lines through L2.  Used when the plane pitch
-  // makes tile rows straddle lines (pitch % 128 != 0 on luma) or when forced; costs a few idle CTA slots.
+  // makes tile rows straddle lines (pitch % 128 != 0 on luma); costs a few idle CTA slots.
   const int chunks = std::max(1, std::min(nf, grid / std::max(1, ntiles)));
-  const bool lockstep = ctx->knobs.comb_part == 1 || (ctx->knobs.comb_part < 0 && (clip->pitch_y % 128) != 0 && chunks * ntiles * 10 >= grid * 9);
+  // Since the tensor maps use 64-byte L2 promotion (straddled lines are no longer fetched whole) the equal-share
+  // partition wins on every layout measured (tools/part_probe.py); lock-step stays available through the knob.
+  const bool lockstep = ctx->knobs.comb_part == 1;
   if (lockstep) grid = chunks * ntiles;
   std::vector<int> seg_start((size_t)grid + 1, 0);
   if (lockstep) {

@@ -12,8 +12,9 @@ for (w, h) in ((1920, 1080), (1440, 1080)):
         synth.make_frames(n0, min(20, n - n0), w, h, device="cuda", out=t[n0:n0 + min(20, n - n0)])
     clip = ab.yv12_clip(t, w, h, n, True)
     ref = None
-    for part in (0, 1):
+    for part, l2 in ((0, 128), (1, 128), (0, 64), (1, 64), (0, 0)):
         os.environ["AMTK_COMB_PART"] = str(part)
+        os.environ["AMTK_COMB_L2"] = str(l2)
         ctx = ab.Context(0, torch.cuda.current_stream().cuda_stream)
         out = ctx.comb_frames(clip)
         torch.cuda.synchronize()
@@ -23,6 +24,6 @@ for (w, h) in ((1920, 1080), (1440, 1080)):
         ms, k = ctx.kernel_timing()
         o = out.cpu().numpy()
         ref = o if ref is None else ref
-        print("%dx%d part=%d: %.3f ms  %.0f GB/s  same=%s" % (w, h, part, ms / k, n * w * h * 1.5 / (ms / k) / 1e6, np.array_equal(o, ref)), flush=True)
+        print("%dx%d part=%d l2=%d: %.3f ms  %.0f GB/s  same=%s" % (w, h, part, l2, ms / k, n * w * h * 1.5 / (ms / k) / 1e6, np.array_equal(o, ref)), flush=True)
         ctx.close()
     del t
