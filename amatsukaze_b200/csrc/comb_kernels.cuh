@@ -32,8 +32,7 @@ constexpr int kCombTW = 128;            // tile width in bytes (= pixels for u8)
 
 // Compile-time shape of one kernel variant: R rows per run (tile height 8R), STRIP pixels per thread-row,
 // STAGES ring slots.
-// ACC selects how threshold hits are counted: 0 = integer masks + IADD3 (ALU pipe), 1 = lshima as fp16 1.0s +
-// HADD2 (FMA pipe), 2 = both numeric (pipe balancing knob; results are identical).
+// ACC is a leftover variant tag (numeric fp16 counting was measured, equal, and removed); always 0.
 template <int R_, int STRIP_, int STAGES_, int ACC_ = 0, int RUNS_ = 8>
 struct CombCfg {
   static constexpr int R = R_, STRIP = STRIP_, STAGES = STAGES_, ACC = ACC_, RUNS = RUNS_;   // RUNS vertical runs per tile
@@ -103,20 +102,21 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t d, uint32_t kM) {
   return (((d & 0x7F7F7F7Fu) + kM) | d) & 0x80808080u;
 }
 
+// Raw per-thread counters of one tile-frame.  slot = row parity RELATIVE to the thread's first row (j & 1); the
+// caller maps slots to fields.  S/L: 8-bit path = pair-coded mask sums (decode_pair after any number of integer
+// additions), 16-bit path = plain counts.  M: 128 per hit.
+struct RawCounts { uint32_t S[2], L[2], M[2]; };
+
 template <typename Cfg, bool EDGE, int PITCH>
-__device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
-                                               int y_first /* global y of this thread's first row */,
-                                               const uint32_t* __restrict__ th_rows /* EDGE: [2][R] thresholds of this run */,
-                                               uint32_t kM, uint32_t thS_bits, uint32_t thL_bits,
-                                               uint32_t& oS, uint32_t& oL, uint32_t& oM) {
+__device__ __forceinline__ RawCounts comb_tile_rows(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
+                                                    const uint32_t* __restrict__ th_rows /* EDGE: [2][R] thresholds of this run */,
+                                                    uint32_t kM, uint32_t thS_bits, uint32_t thL_bits) {
   // cur/prev point at this thread's strip in smem row (run*R) of the box, i.e. global row y_first-2.
   constexpr int R = Cfg::R, NQ = Cfg::NQ, STRIP = Cfg::STRIP;
   const __half2 thS = *reinterpret_cast<const __half2*>(&thS_bits);
   const __half2 thL = *reinterpret_cast<const __half2*>(&thL_bits);
   const __half2 k4 = __float2half2_rn(4.0f), km3 = __float2half2_rn(-3.0f);
-  uint32_t accS[2] = { 0u, 0u }, accL[2] = { 0u, 0u }, accM[2] = { 0u, 0u };
-  __half2 fS[2], fL[2];
-  fS[0] = fS[1] = fL[0] = fL[1] = __float2half2_rn(0.0f);
+  RawCounts c = { { 0u, 0u }, { 0u, 0u }, { 0u, 0u } };
 
   RawRow<STRIP> raw_c, raw_n, rtmp;
   rtmp.load(cur);                 HRow<NQ> h0 = bytes_to_half<STRIP>(rtmp);
@@ -128,7 +128,7 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
     RawRow<STRIP> raw_nn; raw_nn.load(cur + (j + 4) * PITCH);
     const HRow<NQ> h4 = bytes_to_half<STRIP>(raw_nn);
     RawRow<STRIP> pv; pv.load(prev + (j + 2) * PITCH);
-    const int f = j & 1;          // accumulator slot; mapped to the field parity after the loop
+    const int f = j & 1;          // accumulator slot
     // rows y < 2 and y >= H-2 have no comb response (spec): edge tiles read per-row thresholds (infinite there)
     // from a small shared table built once per segment -- two LDS instead of compare/select on the ALU pipe
     __half2 tS = thS, tL = thL;
@@ -139,42 +139,30 @@ __device__ __forceinline__ void comb_tile_rows(const uint8_t* __restrict__ cur, 
 #pragma unroll
     for (int q = 0; q < NQ; q += 2) {
       uint32_t mS[2], mL[2];
-      __half2 nS[2], nL[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         __half2 t = __hadd2(h0.v[q + e], h4.v[q + e]);
         t = __hfma2(k4, h2.v[q + e], t);
         const __half2 u = __hadd2(h1.v[q + e], h3.v[q + e]);
         const __half2 r = __habs2(__hfma2(km3, u, t));
-        if (Cfg::ACC >= 2) nS[e] = __hge2(r, tS); else mS[e] = __hge2_mask(r, tS);
-        if (Cfg::ACC >= 1) nL[e] = __hge2(r, tL); else mL[e] = __hge2_mask(r, tL);
+        mS[e] = __hge2_mask(r, tS);
+        mL[e] = __hge2_mask(r, tL);
       }
-      // integer mode: 0xFFFF-per-lane masks are subtracted as plain 32-bit integers; decode_pair() undoes the
-      // lane coupling.  numeric mode: 1.0s are summed in fp16 (exact: <= 2*R per lane).
-      if (Cfg::ACC >= 2) { fS[f] = __hadd2(fS[f], nS[0]); fS[f] = __hadd2(fS[f], nS[1]); }
-      else accS[f] = accS[f] - mS[0] - mS[1];
-      if (Cfg::ACC >= 1) { fL[f] = __hadd2(fL[f], nL[0]); fL[f] = __hadd2(fL[f], nL[1]); }
-      else accL[f] = accL[f] - mL[0] - mL[1];
+      // 0xFFFF-per-lane masks are subtracted as plain 32-bit integers; decode_pair() undoes the lane coupling
+      c.S[f] = c.S[f] - mS[0] - mS[1];
+      c.L[f] = c.L[f] - mL[0] - mL[1];
     }
     // inter-frame difference of the centre row, 4 pixels per op
 #pragma unroll
     for (int i = 0; i < STRIP / 4; ++i)
-      accM[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.word(i), pv.word(i)), kM), 0x01010101u, accM[f]);
+      c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.word(i), pv.word(i)), kM), 0x01010101u, c.M[f]);
     h0 = h1; h1 = h2; h2 = h3; h3 = h4; raw_c = raw_n; raw_n = raw_nn;
   }
-  // acc = cl + 65536*(ch - cl) (mod 2^32) for lane counts cl, ch  =>  cl + ch = hi16 + 2*lo16
-  auto decode_pair = [](uint32_t a) { return ((a >> 16) + 2u * (a & 0xFFFFu)) & 0xFFFFu; };
-  const int flip = y_first & 1;   // slot 0 holds rows of parity (y_first & 1)
-  auto decode_half = [](__half2 h) { return (uint32_t)(__half2float(__low2half(h)) + __half2float(__high2half(h))); };
-  const uint32_t s0 = Cfg::ACC >= 2 ? decode_half(fS[0]) : decode_pair(accS[0]);
-  const uint32_t s1 = Cfg::ACC >= 2 ? decode_half(fS[1]) : decode_pair(accS[1]);
-  const uint32_t l0 = Cfg::ACC >= 1 ? decode_half(fL[0]) : decode_pair(accL[0]);
-  const uint32_t l1 = Cfg::ACC >= 1 ? decode_half(fL[1]) : decode_pair(accL[1]);
-  const uint32_t m0 = accM[0] >> 7, m1 = accM[1] >> 7;             // dp4a summed 0x80 per hit
-  oS = flip ? (s1 | (s0 << 16)) : (s0 | (s1 << 16));               // top | bottom<<16
-  oL = flip ? (l1 | (l0 << 16)) : (l0 | (l1 << 16));
-  oM = flip ? (m1 | (m0 << 16)) : (m0 | (m1 << 16));
+  return c;
 }
+// acc = cl + 65536*(ch - cl) (mod 2^32) for lane counts cl, ch, and sums of such values keep that form as long as the
+// totals stay below 65536  =>  cl + ch = hi16 + 2*lo16.  Applied ONCE per tile-frame, after the warp/CTA reduction.
+__device__ __forceinline__ uint32_t decode_pair(uint32_t a) { return ((a >> 16) + 2u * (a & 0xFFFFu)) & 0xFFFFu; }
 
 // ---------------------------------------------------------------------------------------------------------
 // 16-bit samples (YUV420P10/12/16): same tile machinery, 4 pixels (8 bytes) per thread-row.  The 5-tap response of
@@ -198,10 +186,9 @@ __device__ __forceinline__ uint32_t halves_ge(uint32_t a, uint32_t b, uint32_t k
 }
 
 template <typename Cfg, bool EDGE, int PITCH>
-__device__ __forceinline__ void comb_tile_rows_u16(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
-                                                   int y_first, const uint32_t* __restrict__ th_rows,
-                                                   uint32_t kM, uint32_t thS_bits, uint32_t thL_bits,
-                                                   uint32_t& oS, uint32_t& oL, uint32_t& oM) {
+__device__ __forceinline__ RawCounts comb_tile_rows_u16(const uint8_t* __restrict__ cur, const uint8_t* __restrict__ prev,
+                                                        const uint32_t* __restrict__ th_rows,
+                                                        uint32_t kM, uint32_t thS_bits, uint32_t thL_bits) {
   constexpr int R = Cfg::R;
   const float thS = __uint_as_float(thS_bits), thL = __uint_as_float(thL_bits);
   float fS[2] = { 0.0f, 0.0f }, fL[2] = { 0.0f, 0.0f };
@@ -232,12 +219,10 @@ __device__ __forceinline__ void comb_tile_rows_u16(const uint8_t* __restrict__ c
     accM[f] = __dp4a(halves_ge(raw_c.y, pv.y, kM), 0x01010101u, accM[f]);
     h0 = h1; h1 = h2; h2 = h3; h3 = h4; raw_c = raw_n; raw_n = raw_nn;
   }
-  const int flip = y_first & 1;
-  const uint32_t s0 = (uint32_t)fS[0], s1 = (uint32_t)fS[1], l0 = (uint32_t)fL[0], l1 = (uint32_t)fL[1];
-  const uint32_t m0 = accM[0] >> 7, m1 = accM[1] >> 7;
-  oS = flip ? (s1 | (s0 << 16)) : (s0 | (s1 << 16));
-  oL = flip ? (l1 | (l0 << 16)) : (l0 | (l1 << 16));
-  oM = flip ? (m1 | (m0 << 16)) : (m0 | (m1 << 16));
+  RawCounts c;
+  c.S[0] = (uint32_t)fS[0]; c.S[1] = (uint32_t)fS[1]; c.L[0] = (uint32_t)fL[0]; c.L[1] = (uint32_t)fL[1];
+  c.M[0] = accM[0]; c.M[1] = accM[1];
+  return c;
 }
 
 template <typename Cfg, int BPS>
@@ -247,19 +232,22 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
   // 128-byte aligned ring base; pointer arithmetic stays on the __shared__ array so loads compile to LDS
   uint8_t* tiles = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t full_bar[S];
-  __shared__ unsigned int red[2][3];
+  __shared__ unsigned int red[2][6];                         // [buffer][field*3 + metric], raw (undecoded) sums
   __shared__ uint32_t th_tab[Cfg::RUNS][2][Cfg::R];          // EDGE tiles: per-row thresholds of every run
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   constexpr int TPR = kCombTW / Cfg::STRIP;       // threads per row
-  const int strip = tid % TPR, run = tid / TPR;
+  static_assert(TPR == 16 && Cfg::RUNS % 4 == 0 && Cfg::THREADS == 16 * Cfg::RUNS, "lane mapping below assumes 16 threads per row");
+  // A warp holds two runs whose first rows have the SAME parity (run, run + RUNS/2: their distance RUNS/2 * R is even),
+  // so "slot 0 / slot 1" of the raw counters means the same field for all 32 lanes and one full-warp REDUX sums them.
+  const int strip = lane & 15, run = (tid >> 5) + (lane >> 4) * (Cfg::RUNS / 2);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 6) (&red[0][0])[tid] = 0u;
+  if (tid < 12) (&red[0][0])[tid] = 0u;
   __syncthreads();
 
   uint32_t gload = 0;      // loads consumed so far by this CTA (ring position of L_0 of the current segment)
@@ -281,9 +269,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
     const int y_first = y0 + run * Cfg::R;
     const bool rows_live = y_first < P.H;            // thread's run intersects the plane
 
-    auto issue = [&](int j) {                        // thread 0 only
-      const uint32_t g = gload + (uint32_t)j;
-      const int st = g % S;
+    auto issue_at = [&](int j, int st) {             // thread 0 only; st = (gload + j) % S
       const int fr = (j == 0) ? fprev : seg.fbegin + j - 1;
       mbar_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
       if (!merged) {
@@ -295,7 +281,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
     };
     if (tid == 0) {
       const int pro = nloads < S ? nloads : S;
-      for (int j = 0; j < pro; ++j) issue(j);
+      for (int j = 0; j < pro; ++j) issue_at(j, (int)((gload + (uint32_t)j) % S));
     }
     if (edge || merged) {                            // (re)build the per-row threshold table of this tile
       for (int i = tid; i < Cfg::RUNS * Cfg::R; i += Cfg::THREADS) {
@@ -307,44 +293,55 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
       }
       __syncthreads();
     }
-    mbar_wait(&full_bar[gload % S], (gload / S) & 1u);      // L_0
+    int stp = (int)(gload % S);                             // ring slot / phase of load g-1, advanced without div/mod
+    uint32_t php = (gload / S) & 1u;
+    mbar_wait(&full_bar[stp], php);                         // L_0
+    const int flip = y_first & 1;                           // slot 0 of this thread's run holds rows of this parity
     for (int k = 1; k <= nf; ++k) {
-      const uint32_t g = gload + (uint32_t)k;
-      const int st = g % S, stp = (g - 1) % S;
-      mbar_wait(&full_bar[st], (g / S) & 1u);
-      uint32_t vS = 0, vL = 0, vM = 0;
+      int st = stp + 1; uint32_t ph = php;
+      if (st == S) { st = 0; ph ^= 1u; }
+      mbar_wait(&full_bar[st], ph);
+      RawCounts c = { { 0u, 0u }, { 0u, 0u }, { 0u, 0u } };
       if (!merged) {
         const uint8_t* cur = tiles + st * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
         const uint8_t* prv = tiles + stp * Cfg::STAGE_BYTES + (run * Cfg::R) * kCombTW + strip * Cfg::STRIP;
         if (!edge) {
-          if (BPS == 1) comb_tile_rows<Cfg, false, kCombTW>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
-          else comb_tile_rows_u16<Cfg, false, kCombTW>(cur, prv, y_first, nullptr, P.thM, P.thS, P.thL, vS, vL, vM);
+          if (BPS == 1) c = comb_tile_rows<Cfg, false, kCombTW>(cur, prv, nullptr, P.thM, P.thS, P.thL);
+          else c = comb_tile_rows_u16<Cfg, false, kCombTW>(cur, prv, nullptr, P.thM, P.thS, P.thL);
         } else if (rows_live) {
-          if (BPS == 1) comb_tile_rows<Cfg, true, kCombTW>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
-          else comb_tile_rows_u16<Cfg, true, kCombTW>(cur, prv, y_first, &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+          if (BPS == 1) c = comb_tile_rows<Cfg, true, kCombTW>(cur, prv, &th_tab[run][0][0], P.thM, P.thS, P.thL);
+          else c = comb_tile_rows_u16<Cfg, true, kCombTW>(cur, prv, &th_tab[run][0][0], P.thM, P.thS, P.thL);
         }
       } else if (rows_live) {                        // half-width sub-tiles: row pitch 64 bytes
         constexpr int HP = kCombTW / 2, HTPR = HP / Cfg::STRIP;
         const int off = (strip / HTPR) * (Cfg::STAGE_BYTES / 2) + (run * Cfg::R) * HP + (strip % HTPR) * Cfg::STRIP;
-        if (BPS == 1) comb_tile_rows<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off, y_first,
-                                                    &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
-        else comb_tile_rows_u16<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off, y_first,
-                                               &th_tab[run][0][0], P.thM, P.thS, P.thL, vS, vL, vM);
+        if (BPS == 1) c = comb_tile_rows<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off,
+                                                        &th_tab[run][0][0], P.thM, P.thS, P.thL);
+        else c = comb_tile_rows_u16<Cfg, true, HP>(tiles + st * Cfg::STAGE_BYTES + off, tiles + stp * Cfg::STAGE_BYTES + off,
+                                                   &th_tab[run][0][0], P.thM, P.thS, P.thL);
       }
-      vS = __reduce_add_sync(0xFFFFFFFFu, vS);
-      vL = __reduce_add_sync(0xFFFFFFFFu, vL);
-      vM = __reduce_add_sync(0xFFFFFFFFu, vM);
+      // Raw (still pair-coded) counters are summed per warp, then per CTA in shared memory; decoding happens once per
+      // tile-frame in the six writer threads.
+      const uint32_t rM0 = __reduce_add_sync(0xFFFFFFFFu, c.M[0]), rM1 = __reduce_add_sync(0xFFFFFFFFu, c.M[1]);
+      const uint32_t rS0 = __reduce_add_sync(0xFFFFFFFFu, c.S[0]), rS1 = __reduce_add_sync(0xFFFFFFFFu, c.S[1]);
+      const uint32_t rL0 = __reduce_add_sync(0xFFFFFFFFu, c.L[0]), rL1 = __reduce_add_sync(0xFFFFFFFFu, c.L[1]);
       const int rb = gstep & 1;
-      if (lane == 0) { atomicAdd(&red[rb][0], vM); atomicAdd(&red[rb][1], vS); atomicAdd(&red[rb][2], vL); }
-      __syncthreads();                               // all reads of stage stp done; red[rb] complete
-      if (tid < 3) {
-        const unsigned v = atomicExch(&red[rb][tid], 0u);          // packed top | bottom<<16
-        int* o = a.counts + (size_t)(seg.fbegin + k - 1 - a.out_frame0) * 12 + P.cls * 6 + tid;
-        if (v & 0xFFFFu) atomicAdd(o, (int)(v & 0xFFFFu));         // top field   [metric]
-        if (v >> 16) atomicAdd(o + 3, (int)(v >> 16));             // bottom field [metric]
+      if (lane == 0) {
+        unsigned int* r0 = &red[rb][flip * 3];       // slot 0 -> field `flip`, slot 1 -> the other one
+        unsigned int* r1 = &red[rb][(flip ^ 1) * 3];
+        atomicAdd(r0 + 0, rM0); atomicAdd(r0 + 1, rS0); atomicAdd(r0 + 2, rL0);
+        atomicAdd(r1 + 0, rM1); atomicAdd(r1 + 1, rS1); atomicAdd(r1 + 2, rL1);
       }
-      if (tid == 0 && (k - 1 + S) < nloads) issue(k - 1 + S);
+      __syncthreads();                               // all reads of stage stp done; red[rb] complete
+      if (tid < 6) {                                 // tid = field*3 + metric = the counts[] layout of one class
+        unsigned v = atomicExch(&red[rb][tid], 0u);
+        const int metric = tid >= 3 ? tid - 3 : tid;
+        v = metric == 0 ? (v >> 7) : (BPS == 1 ? decode_pair(v) : v);
+        if (v) atomicAdd(a.counts + (size_t)(seg.fbegin + k - 1 - a.out_frame0) * 12 + P.cls * 6 + tid, (int)v);
+      }
+      if (tid == 0 && (k - 1 + S) < nloads) issue_at(k - 1 + S, stp);     // refill the slot that was just released
       ++gstep;
+      stp = st; php = ph;
     }
     gload += (uint32_t)nloads;
   }
