@@ -246,7 +246,7 @@ static const CombVariant* comb_variants(int* n) {
     // production: rows-per-run chosen per clip (pick_comb_R), 8-byte strips, 3-stage ring, integer mask counting
     make_variant16<CombCfg<15, 8, 3, 0>>(), make_variant16<CombCfg<16, 8, 3, 0>>(), make_variant16<CombCfg<17, 8, 3, 0>>(),
     // kept for tools/tune_comb.py (all measured within 1 % of, or below, the production variant)
-    make_variant<CombCfg<17, 8, 2, 0>>(), make_variant<CombCfg<17, 8, 4, 0>>(),
+    make_variant<CombCfg<17, 8, 2, 0>>(), make_variant<CombCfg<17, 8, 4, 0>>(), make_variant<CombCfg<17, 8, 3, 1>>(),
   };
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;

@@ -32,7 +32,9 @@ constexpr int kCombTW = 128;            // tile width in bytes (= pixels for u8)
 
 // Compile-time shape of one kernel variant: R rows per run (tile height 8R), STRIP pixels per thread-row,
 // STAGES ring slots.
-// ACC is a leftover variant tag (numeric fp16 counting was measured, equal, and removed); always 0.
+// ACC_ now selects the end-of-step synchronisation: 0 = one block barrier per tile-frame; 1 = "release" mode: every
+// warp arrives on a per-slot mbarrier when it is done with the previous-frame slot and runs ahead (by at most one
+// step), only warp 0 waits for all arrivals, flushes the counters and refills the slot.
 template <int R_, int STRIP_, int STAGES_, int ACC_ = 0, int RUNS_ = 8>
 struct CombCfg {
   static constexpr int R = R_, STRIP = STRIP_, STAGES = STAGES_, ACC = ACC_, RUNS = RUNS_;   // RUNS vertical runs per tile
@@ -232,6 +234,9 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
   // 128-byte aligned ring base; pointer arithmetic stays on the __shared__ array so loads compile to LDS
   uint8_t* tiles = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t full_bar[S];
+  __shared__ __align__(8) uint64_t empty_bar[S];
+  constexpr bool kRelease = Cfg::ACC == 1;
+  uint32_t ephase = 0;                                       // warp 0: parity to wait for on each empty_bar, one bit per slot
   __shared__ unsigned int red[2][6];                         // [buffer][field*3 + metric], raw (undecoded) sums
   __shared__ uint32_t th_tab[Cfg::RUNS][2][Cfg::R];          // EDGE tiles: per-row thresholds of every run
 
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
   const int strip = lane & 15, run = (tid >> 5) + (lane >> 4) * (Cfg::RUNS / 2);
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], Cfg::THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 12) (&red[0][0])[tid] = 0u;
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
   uint32_t gstep = 0;      // tile-frames processed so far (selects the red[] buffer)
   const int seg_lo = a.seg_start[blockIdx.x], seg_hi = a.seg_start[blockIdx.x + 1];
   for (int si = seg_lo; si < seg_hi; ++si) {
+    if (kRelease && si > seg_lo) __syncthreads();    // th_tab / ring slots of the previous segment are no longer read
     const CombSegment seg = a.segs[si];
     const int pl = (seg.tile >= a.plane[3].tile0) ? 3 : (seg.tile >= a.plane[2].tile0) ? 2 : (seg.tile >= a.plane[1].tile0) ? 1 : 0;
     const CombPlane& P = a.plane[pl];
@@ -332,12 +338,24 @@ __global__ void __launch_bounds__(Cfg::THREADS) comb_tma_kernel(const __grid_con
         atomicAdd(r0 + 0, rM0); atomicAdd(r0 + 1, rS0); atomicAdd(r0 + 2, rL0);
         atomicAdd(r1 + 0, rM1); atomicAdd(r1 + 1, rS1); atomicAdd(r1 + 2, rL1);
       }
-      __syncthreads();                               // all reads of stage stp done; red[rb] complete
-      if (tid < 6) {                                 // tid = field*3 + metric = the counts[] layout of one class
+      auto flush = [&]() {                           // tid = field*3 + metric = the counts[] layout of one class
         unsigned v = atomicExch(&red[rb][tid], 0u);
         const int metric = tid >= 3 ? tid - 3 : tid;
         v = metric == 0 ? (v >> 7) : (BPS == 1 ? decode_pair(v) : v);
         if (v) atomicAdd(a.counts + (size_t)(seg.fbegin + k - 1 - a.out_frame0) * 12 + P.cls * 6 + tid, (int)v);
+      };
+      if (!kRelease) {
+        __syncthreads();                             // all reads of stage stp done; red[rb] complete
+        if (tid < 6) flush();
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stp]); // this warp: done with slot stp, its sums are in red[rb]
+        if (tid < 32) {
+          mbar_wait(&empty_bar[stp], (ephase >> stp) & 1u);
+          ephase ^= 1u << stp;
+          if (tid < 6) flush();
+          __syncwarp();
+        }
       }
       if (tid == 0 && (k - 1 + S) < nloads) issue_at(k - 1 + S, stp);     // refill the slot that was just released
       ++gstep;
