@@ -209,6 +209,8 @@ __device__ __forceinline__ RawCounts comb_tile_rows_u16(const uint8_t* __restric
     const int f = j & 1;
     float tS = thS, tL = thL;
     if (EDGE) { tS = __uint_as_float(th_rows[j]); tL = __uint_as_float(th_rows[R + j]); }
+    accM[f] = __dp4a(halves_ge(raw_c.x, pv.x, kM), 0x01010101u, accM[f]);    // difference first, as in the 8-bit path
+    accM[f] = __dp4a(halves_ge(raw_c.y, pv.y, kM), 0x01010101u, accM[f]);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float t = h0.v[q] + h4.v[q];
@@ -218,8 +220,6 @@ __device__ __forceinline__ RawCounts comb_tile_rows_u16(const uint8_t* __restric
       fS[f] += (r >= tS) ? 1.0f : 0.0f;
       fL[f] += (r >= tL) ? 1.0f : 0.0f;
     }
-    accM[f] = __dp4a(halves_ge(raw_c.x, pv.x, kM), 0x01010101u, accM[f]);
-    accM[f] = __dp4a(halves_ge(raw_c.y, pv.y, kM), 0x01010101u, accM[f]);
     h0 = h1; h1 = h2; h2 = h3; h3 = h4; raw_c = raw_n; raw_n = raw_nn;
   }
   RawCounts c;

@@ -9,6 +9,8 @@ import numpy as np
 import torch
 import amatsukaze_b200 as ab
 from amatsukaze_b200 import synth
+if os.environ.get("AMTK_LIB"):
+    ab.capi.LIB_PATH = os.environ["AMTK_LIB"]      # codegen experiments: load another build of the library
 
 
 def timed(fn, reps=5):
