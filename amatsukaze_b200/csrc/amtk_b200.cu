@@ -231,21 +231,22 @@ static int comb_thresholds_ok(const amtk_comb_params* p, int bytes_per_sample) {
 
 // Everything the host needs to know about one compiled comb-kernel variant.
 struct CombVariant {
-  int R, strip, stages, acc, TH, boxH, threads, smem;
+  int R, strip, stages, sync, TH, boxH, threads, smem;
   void (*kernel)(const CombArgs);        // 8-bit samples
   void (*kernel16)(const CombArgs);      // 16-bit samples (only for the default variants; else NULL)
 };
 template <typename Cfg> static CombVariant make_variant() {
-  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::ACC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_tma_kernel<Cfg, 1>, nullptr };
+  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::SYNC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_tma_kernel<Cfg, 1>, nullptr };
 }
 template <typename Cfg> static CombVariant make_variant16() {     // 8-byte strips: 8 px of u8 or 4 px of u16
-  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::ACC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_tma_kernel<Cfg, 1>, comb_tma_kernel<Cfg, 2> };
+  return CombVariant{ Cfg::R, Cfg::STRIP, Cfg::STAGES, Cfg::SYNC, Cfg::TH, Cfg::BOXH, Cfg::THREADS, Cfg::SMEM, comb_tma_kernel<Cfg, 1>, comb_tma_kernel<Cfg, 2> };
 }
 static const CombVariant* comb_variants(int* n) {
   static const CombVariant v[] = {
-    // production: rows-per-run chosen per clip (pick_comb_R), 8-byte strips, 3-stage ring, integer mask counting
+    // production: rows-per-run chosen per clip (pick_comb_R), 8-byte strips, 3-stage ring, block barrier per tile-frame
     make_variant16<CombCfg<15, 8, 3, 0>>(), make_variant16<CombCfg<16, 8, 3, 0>>(), make_variant16<CombCfg<17, 8, 3, 0>>(),
-    // kept for tools/tune_comb.py (all measured within 1 % of, or below, the production variant)
+    // kept for tools/tune_comb.py: 2- and 4-stage rings, mbarrier 'release' sync (all measured below the production
+    // variant)
     make_variant<CombCfg<17, 8, 2, 0>>(), make_variant<CombCfg<17, 8, 4, 0>>(), make_variant<CombCfg<17, 8, 3, 1>>(),
   };
   *n = (int)(sizeof(v) / sizeof(v[0]));
@@ -299,7 +300,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   const int hY = clip->height, hC = clip->height >> clip->log_uvy;
   const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_comb_R(hY, hC);
   int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
-  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == ctx->knobs.comb_strip && vars[i].stages == ctx->knobs.comb_stages && vars[i].acc == ctx->knobs.comb_acc) V = &vars[i];
+  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].strip == ctx->knobs.comb_strip && vars[i].stages == ctx->knobs.comb_stages && vars[i].sync == ctx->knobs.comb_sync) V = &vars[i];
   if (!V) AMTK_FAIL("comb: no kernel variant for the requested AMTK_COMB_* settings");
   const int bps = clip->bytes_per_sample;
   if (bps == 2 && !V->kernel16) AMTK_FAIL("comb: the selected AMTK_COMB_* variant has no 16-bit kernel");
@@ -469,7 +470,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_STAGES")) c->knobs.comb_stages = atoi(e);
   if (const char* e = getenv("AMTK_COMB_R")) c->knobs.comb_R = atoi(e);
   if (const char* e = getenv("AMTK_COMB_CTAS")) c->knobs.comb_ctas = atoi(e);
-  if (const char* e = getenv("AMTK_COMB_ACC")) c->knobs.comb_acc = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_SYNC")) c->knobs.comb_sync = atoi(e);
   if (const char* e = getenv("AMTK_COMB_GENERIC")) c->knobs.comb_generic = atoi(e);
   if (const char* e = getenv("AMTK_COMB_MERGE_UV")) c->knobs.comb_merge_uv = atoi(e);
   if (const char* e = getenv("AMTK_COMB_PART")) c->knobs.comb_part = atoi(e);

@@ -64,7 +64,7 @@ struct amtk_ctx {
     int comb_generic = 0;   // 1: force the plain-load comb kernel
     int comb_merge_uv = 1;  // U|V remainder columns share one tile
     int comb_part = -1;     // partition: -1 auto, 0 equal-share, 1 lock-step
-    int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_acc = 0, comb_l2 = 64;
+    int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_sync = 0, comb_l2 = 64;
   } knobs;
   // optional per-launch timing of the dominant (comb) kernel with CUDA events on the launching stream
   bool timing = false;

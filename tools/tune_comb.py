@@ -28,7 +28,7 @@ for strip, stages, ctas, acc, l2, R in combos:
     os.environ["AMTK_COMB_STRIP"] = str(strip)
     os.environ["AMTK_COMB_STAGES"] = str(stages)
     os.environ["AMTK_COMB_CTAS"] = str(ctas)
-    os.environ["AMTK_COMB_ACC"] = str(acc)
+    os.environ["AMTK_COMB_SYNC"] = str(acc)
     os.environ["AMTK_COMB_L2"] = str(l2)
     os.environ["AMTK_COMB_R"] = str(R)
     ctx = ab.Context(0, torch.cuda.current_stream().cuda_stream)
@@ -42,5 +42,5 @@ for strip, stages, ctas, acc, l2, R in combos:
     if ref is None:
         ref = o
     gbs = frames * W * H * 1.5 / (ms / n * 1e-3) / 1e9
-    print("strip=%d stages=%d ctas=%d acc=%d l2=%d R=%d: %.3f ms/launch  %.0f GB/s  %.0f fps  same=%s" % (strip, stages, ctas, acc, l2, R, ms / n, gbs, frames / (ms / n * 1e-3), np.array_equal(o, ref)), flush=True)
+    print("strip=%d stages=%d ctas=%d sync=%d l2=%d R=%d: %.3f ms/launch  %.0f GB/s  %.0f fps  same=%s" % (strip, stages, ctas, acc, l2, R, ms / n, gbs, frames / (ms / n * 1e-3), np.array_equal(o, ref)), flush=True)
     ctx.close()
