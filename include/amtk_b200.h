@@ -17,6 +17,7 @@
  */
 #ifndef AMTK_B200_H
 #define AMTK_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {

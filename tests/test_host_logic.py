@@ -131,3 +131,22 @@ def test_argument_validation(native_lib):
         raw.deint().create_mask(0.0)
     p = ab.default_comb_params()
     assert p.as_list() == [20, 12, 36, 24, 16, 48]
+
+
+def test_c_abi_header_is_plain_c_and_cxx(tmp_path):
+    """include/amtk_b200.h is the drop-in boundary: it must compile as C99 and as C++ with nothing but the standard
+    headers (no torch / CUDA types in the signatures)."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "amtk_b200.h")
+    for comp, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "c++")):
+        r = subprocess.run([comp, std, "-x", lang, "-fsyntax-only", "-Wall", "-Werror", "-pedantic", hdr],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_host_filter_sources_compile(tmp_path):
+    """The C++ mirror of the reference's filter interface compiles against the C ABI alone (no CUDA headers)."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "test_filters.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
