@@ -73,5 +73,23 @@ def build_host_test(force=False):
     return HOST_TEST
 
 
+HOST_ONLY_TEST = os.path.join(PKG, "..", "tests", "cpp", "test_host_only")
+
+
+def build_host_only_test(force=False):
+    """tests/cpp/test_host_only: driver of the host-side logic that needs no device (CPU test suite)."""
+    src = os.path.join(PKG, "..", "tests", "cpp", "test_host_only.cpp")
+    deps = [src, os.path.join(PKG, "host", "filters.hpp"), os.path.join(PKG, "host", "avs_compat.h"), LIB]
+    if (not force and os.path.exists(HOST_ONLY_TEST) and all(os.path.getmtime(HOST_ONLY_TEST) >= os.path.getmtime(d) for d in deps)):
+        return HOST_ONLY_TEST
+    cmd = ["g++", "-std=c++17", "-O2", "-o", HOST_ONLY_TEST, src, "-L" + LIBDIR, "-lamtk_b200",
+           "-Wl,-rpath,$ORIGIN/../../amatsukaze_b200/lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("host-only test build failed")
+    return HOST_ONLY_TEST
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -375,6 +375,14 @@ public:
   }
 
   const float* results() const { return reinterpret_cast<const float*>(evalResults.data()); }
+  // Offline re-analysis of saved scores: float[nframes][numLogos][2] as scanFrames produces them (the reference can only
+  // dump them, dumpResult :1632-1645).  Lets selectLogo / writeResult run without a device.
+  void setResults(const float* corr, int nframes, unsigned fps_numerator, unsigned fps_denominator) {
+    evalResults.resize((size_t)nframes * numLogos);
+    memcpy(evalResults.data(), corr, evalResults.size() * sizeof(EvalResult));
+    numFrames = nframes;
+    framesPerSec = (int)std::round((float)fps_numerator / fps_denominator);
+  }
 
   // choose the logo that is detected most often with the least residue after removal (:1647-1682)
   void selectLogo(int numCandidates = -1) {

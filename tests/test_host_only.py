@@ -1,0 +1,184 @@
+"""Host-side logic of the filter mirror that needs no device (tests/cpp/test_host_only.cpp): LogoFrame::selectLogo /
+writeResult against the reference's own code (oracle/_ref, LogoScan.hpp:1645-1827 compiled verbatim), AMTEraseLogo's
+logoframe state machine + fade selection against the oracle's CalcFade2, AMTDecimate, the timecode reader and the
+telecine side files.  CPU suite."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import amatsukaze_b200 as ab
+from amatsukaze_b200 import _build, synth
+from oracle import pyoracle as po
+
+
+@pytest.fixture(scope="module")
+def exe():
+    return _build.build_host_only_test()
+
+
+def run(exe, *args, ok=(0,)):
+    r = subprocess.run([exe, *[str(a) for a in args]], capture_output=True, text=True, timeout=120)
+    assert r.returncode in ok, (r.returncode, r.stdout, r.stderr)
+    return r
+
+
+def score_track(rng, n, on_ranges, noise=0.08, flicker=0.0):
+    """(n, 2) corr0/corr1 as ScanFrame produces them: logo present -> corr0 high, corr1 ~ 0; absent -> corr0 ~ 0, corr1 < 0."""
+    on = np.zeros(n, bool)
+    for a, b in on_ranges:
+        on[a:b] = True
+    if flicker:
+        on ^= rng.random(n) < flicker
+    c0 = np.where(on, 0.8, 0.0) + rng.normal(0, noise, n)
+    c1 = np.where(on, 0.0, -0.8) + rng.normal(0, noise, n)
+    return np.stack([c0, c1], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("fps", [(24000, 1001), (30000, 1001), (60000, 1001), (25, 1)])
+def test_logoframe_select_and_write_match_reference(exe, tmp_path, fps):
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(fps[0])
+    n = 700
+    cases = [
+        [[(100, 400)], [(0, 0)]],                                   # one section, second logo never present
+        [[(0, 250), (400, 700)], [(50, 120)]],                      # starts and ends inside a section
+        [[(60, 90), (130, 170), (300, 650)], [(0, 700)]],           # short sections, always-on competitor
+        [[(0, 0)], [(0, 0)]],                                       # nothing anywhere
+        [[(0, 700)], [(200, 500)]],                                 # everything
+        [[(200, 210), (215, 500)], [(10, 20)]],                     # a gap shorter than the filters
+    ]
+    for ci, (a, b) in enumerate(cases):
+        for flicker in (0.0, 0.03):
+            ev = np.stack([score_track(rng, n, a, flicker=flicker), score_track(rng, n, b, flicker=flicker)], 1)   # (n, 2 logos, 2)
+            sp, op, rp = tmp_path / "s.bin", tmp_path / "o.txt", tmp_path / "r.txt"
+            ev.tofile(sp)
+            r = run(exe, "logoframe", sp, n, 2, fps[0], fps[1], op)
+            best, ratio = po.ref_logoframe(ev, int(round(fps[0] / fps[1])), str(rp))
+            assert ("bestLogo=%d " % best) in r.stdout, (ci, flicker, r.stdout, best)
+            got_ratio = float(r.stdout.split("logoRatio=")[1])
+            assert np.float32(got_ratio) == np.float32(ratio)
+            assert open(op).read() == open(rp).read(), (ci, flicker)
+
+
+def test_timecode_reader(exe, tmp_path):
+    # explicit total, comments, CRLF
+    p = tmp_path / "a.txt"
+    p.write_bytes(b"# timecode format v2\r\n0\r\n33\r\n67\r\n\r\n# total: 0.1001\r\n999\r\n")
+    out = run(exe, "timecode", p).stdout.split()
+    assert out[:3] == ["ok=1", "n=4", "fps=0"] or out[:2] == ["ok=1", "n=4"]
+    assert [float(x) for x in out[3:]] == [0.0, 33.0, 67.0, pytest.approx(100.1)]
+    # no total: the end time is extrapolated from the last two stamps
+    p.write_text("0\n42\n83\n")
+    out = run(exe, "timecode", p).stdout.split()
+    assert [float(x) for x in out[3:]] == [0.0, 42.0, 83.0, 124.0]
+    # a single stamp: one 60 fps frame is appended
+    p.write_text("500\n")
+    out = run(exe, "timecode", p).stdout.split()
+    assert [float(x) for x in out[3:]] == [500.0, pytest.approx(500 + 1000 / 60, abs=1e-5)]
+    # stamps on the 120000/1001 grid are recognised as 120 fps VFR timing (FilteredSource.hpp:190-211)
+    grid = [int(round(k * 1001 / 120.0)) for k in (0, 5, 9, 14, 18, 23, 27, 32, 36)]
+    p.write_text("".join("%d\n" % t for t in grid))
+    assert "fps=120" in run(exe, "timecode", p).stdout or "fps=240" in run(exe, "timecode", p).stdout
+    # missing file / empty file
+    assert "ok=0" in run(exe, "timecode", tmp_path / "nope.txt").stdout
+    p.write_text("")
+    assert "ok=1 n=0" in run(exe, "timecode", p).stdout
+
+
+def test_decimate_map_and_mismatch(exe, tmp_path):
+    d = tmp_path / "d.txt"
+    d.write_text("".join("%d\n" % v for v in [1, 1, 2, 1] * 3 + [1, 1]))
+    out = run(exe, "decimate", d, 17).stdout
+    assert out.startswith("frames=14 map: 0 1 2 4 5 6 7 9 10 11 12 14 15 16")
+    r = run(exe, "decimate", d, 18, ok=(4,))                       # AMTSource.hpp-style error text
+    assert "# of frames does not match. 17(" in r.stdout and "vs 18(source clip)" in r.stdout
+    r = run(exe, "decimate", tmp_path / "missing.txt", 5, ok=(4,))
+    assert "failed to open" in r.stdout
+
+
+def test_telecine_side_files_from_counts(exe, tmp_path):
+    n = 43
+    counts = np.zeros((n, 12), np.int32)
+    counts[:, 2] = 40
+    counts[:, 5] = 35
+    film = []
+    for c in range(2, n - 4, 5):                                   # combed pairs at frames c, c+1 (phase 2) ...
+        if (c // 5) % 3 != 2:                                      # ... except every third cycle (video insert)
+            counts[c, 2] = counts[c, 5] = 5000
+            counts[c + 1, 2] = counts[c + 1, 5] = 4000
+            film.append(c)
+    cp = tmp_path / "c.bin"
+    counts.tofile(cp)
+    r = run(exe, "telecine", cp, n, 30000, 1001, tmp_path / "tc")
+    assert ("film_cycles=%d" % len(film)) in r.stdout
+    dur = [int(x) for x in open(tmp_path / "tc.duration.txt").read().split()]
+    assert sum(dur) == n and len(dur) == n - len(film)
+    # every film cycle is 1,1,2,1 with the long frame starting on the first combed frame
+    starts = np.concatenate([[0], np.cumsum(dur)[:-1]])
+    assert sorted(int(s) for s, d in zip(starts, dur) if d == 2) == film
+    # the timecode file holds one stamp per output frame and the total; the reader recovers both
+    out = run(exe, "timecode", tmp_path / "tc.timecode.txt").stdout.split()
+    stamps = [float(x) for x in out[3:]]
+    assert len(stamps) == len(dur) + 1
+    assert stamps[-1] == pytest.approx(n * 1001 / 30.0, abs=1e-3)
+    assert stamps[:-1] == [float(int(np.floor(s * 1001 / 30.0 + 0.5))) for s in starts]     # std::round: half away from zero
+    # decimate accepts its own duration file
+    assert run(exe, "decimate", tmp_path / "tc.duration.txt", n).stdout.startswith("frames=%d " % len(dur))
+
+
+def _frame_result(n, elems):
+    fr = np.zeros(n, np.int32)
+
+    def fill(a, b, v):
+        a = min(n, a)
+        b = min(n, max(a, b))
+        fr[a:b] = v
+    for (sb, ss, se), (eb, es, ee) in elems:
+        fill(ss, se + 1, 1)
+        fill(se, es + 1, 2)
+        fill(es + 1, ee + 1, 1)
+    return fr
+
+
+def test_eraselogo_fade_selection(exe, tmp_path):
+    n, maxfade = 120, 16
+    rng = np.random.default_rng(11)
+    rec = rng.normal(0.0, 0.5, (n, 33)).astype(np.float32)
+    rp = tmp_path / "rec.bin"
+    rec.tofile(rp)
+    lg = synth.make_logo(32, 32, seed=2)
+    lp = str(tmp_path / "logo.lgd")
+    ab.Logo.create(lg["data"], 32, 32, 64, 32, 8, 0).save(lp, "t", 1)
+    # without a logoframe file every frame goes through CalcFade2 (LogoScan.hpp:1263-1315)
+    fp = tmp_path / "f0.bin"
+    run(exe, "fades", lp, "-", rp, n, maxfade, fp)
+    got = np.fromfile(fp, np.float32).reshape(n, 2)
+    want = np.array([po.or_calc_fade2(rec, n, i) for i in range(n)], np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # with one: frames whose +-maxfade/2 neighbourhood has a uniform state take 0 / 1 directly (:1317-1341)
+    elems = [((22, 20, 26), (58, 55, 61)), ((90, 88, 93), (118, 115, 119))]
+    lf = tmp_path / "logof.txt"
+    lf.write_text("".join("%6d S 0 ALL %6d %6d\n%6d E 0 ALL %6d %6d\n" % (*s, *e) for s, e in elems))
+    run(exe, "fades", lp, lf, rp, n, maxfade, fp)
+    got = np.fromfile(fp, np.float32).reshape(n, 2)
+    fr = _frame_result(n, elems)
+    half = maxfade >> 1
+    direct = 0
+    for i in range(n):
+        win = fr[np.clip(np.arange(i - half, i + half + 1), 0, n - 1)]
+        if np.all(win == win[0]):
+            exp = (1.0, 1.0) if fr[i] == 2 else (0.0, 0.0)
+            direct += 1
+        else:
+            exp = po.or_calc_fade2(rec, n, i)
+        assert tuple(np.float32(exp)) == tuple(got[i]), i
+    assert 0 < direct < n
+    # malformed files are rejected with the reference's message
+    lf.write_text("%6d S 0 ALL %6d %6d\n%6d S 0 ALL %6d %6d\n" % (22, 20, 26, 58, 55, 61))
+    r = run(exe, "fades", lp, lf, rp, n, maxfade, fp, ok=(4,))
+    assert "Start and End must be cyclic" in r.stdout
+    r = run(exe, "fades", tmp_path / "none.lgd", "-", rp, n, maxfade, fp, ok=(4,))
+    assert "Failed to read logo file" in r.stdout
