@@ -41,9 +41,10 @@ static bool ensure(void** p, size_t* cap, size_t need) {
   return true;
 }
 
-struct DevSelect {   // RAII: make the context's device current for the duration of a call
+struct DevSelect {   // RAII: make a device (the context's, or an ordinal) current for the duration of a call
   int prev = -1; bool ok = true;
-  explicit DevSelect(const amtk_ctx* c) { ok = cuda_ok(cudaGetDevice(&prev), "cudaGetDevice") && cuda_ok(cudaSetDevice(c->device), "cudaSetDevice"); }
+  explicit DevSelect(const amtk_ctx* c) : DevSelect(c->device) {}
+  explicit DevSelect(int device) { ok = cuda_ok(cudaGetDevice(&prev), "cudaGetDevice") && cuda_ok(cudaSetDevice(device), "cudaSetDevice"); }
   ~DevSelect() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
@@ -632,8 +633,8 @@ static int logo_upload_tables(amtk_logo* l) {
 static int logo_ensure_device(const amtk_logo* cl, amtk_ctx* ctx, bool need_tables) {
   amtk_logo* l = const_cast<amtk_logo*>(cl);
   std::lock_guard<std::mutex> lock(l->mu);
-  if (l->ctx && l->ctx->device != ctx->device) AMTK_FAIL("logo already resident on another device");
-  if (!l->ctx) l->ctx = ctx;
+  if (l->device >= 0 && l->dA && l->device != ctx->device) AMTK_FAIL("logo already resident on another device");
+  l->device = ctx->device;
   if (!l->dA && !logo_upload_planes(l)) return 0;
   if (need_tables) {
     if (!l->has_mask) AMTK_FAIL("logo has no mask: call amtk_logo_create_mask first");
@@ -642,9 +643,9 @@ static int logo_ensure_device(const amtk_logo* cl, amtk_ctx* ctx, bool need_tabl
   return 1;
 }
 
-static int logo_adopt(amtk_ctx* ctx, amtk::HostLogo&& h, amtk_logo** out) {
+static int logo_adopt(amtk_ctx* /*ctx: logos bind to a device on first use*/, amtk::HostLogo&& h, amtk_logo** out) {
   amtk_logo* l = new amtk_logo();
-  l->ctx = ctx; l->host = std::move(h);
+  l->host = std::move(h);
   *out = l;
   return 1;
 }
@@ -674,21 +675,21 @@ int amtk_logo_save(const amtk_logo* l, const char* path, const char* name, int s
 
 void amtk_logo_destroy(amtk_logo* l) {
   if (!l) return;
-  if (l->ctx && l->dA) { DevSelect ds(l->ctx); logo_free_device(l); }
+  if (l->device >= 0 && l->dA) { DevSelect ds(l->device); logo_free_device(l); }
   delete l;
 }
 
 int amtk_logo_deint(const amtk_logo* src, amtk_logo** out) {
   if (!src || !out) AMTK_FAIL("amtk_logo_deint: null argument");
   amtk::HostLogo d; amtk::logo_deint(src->host, d);
-  return logo_adopt(src->ctx, std::move(d), out);
+  return logo_adopt(nullptr, std::move(d), out);
 }
 
 int amtk_logo_field(const amtk_logo* src, int bottom, amtk_logo** out) {
   if (!src || !out) AMTK_FAIL("amtk_logo_field: null argument");
   if (src->host.h / 2 < 5) AMTK_FAIL("amtk_logo_field: logo too small");
   amtk::HostLogo f; amtk::logo_field(src->host, bottom != 0, f);
-  return logo_adopt(src->ctx, std::move(f), out);
+  return logo_adopt(nullptr, std::move(f), out);
 }
 
 int amtk_logo_create_mask(amtk_logo* l, float maskratio) {
@@ -873,7 +874,7 @@ int amtk_scan_create(amtk_ctx* ctx, int scanw, int scanh, int lx, int ly, int th
   if (scanw < 4 || scanh < 4 || scanw > 4096 || scanh > 4096 || lx < 0 || lx > 2 || ly < 0 || ly > 2) AMTK_FAIL("amtk_scan_create: bad geometry");
   DevSelect ds(ctx); if (!ds.ok) return 0;
   amtk_scan* s = new amtk_scan();
-  s->ctx = ctx; s->scanw = scanw; s->scanh = scanh; s->logUVx = lx; s->logUVy = ly; s->thy = thy;
+  s->ctx = ctx; s->device = ctx->device; s->scanw = scanw; s->scanh = scanh; s->logUVx = lx; s->logUVy = ly; s->thy = thy;
   s->npix = (size_t)scanw * scanh + 2 * (size_t)(scanw >> lx) * (scanh >> ly);
   if (!cuda_ok(cudaMalloc(&s->dSums, s->npix * 3 * sizeof(unsigned long long)), "cudaMalloc") ||
       !cuda_ok(cudaMalloc(&s->dBg, 8 * sizeof(unsigned long long)), "cudaMalloc")) { amtk_scan_destroy(s); return 0; }
@@ -885,7 +886,7 @@ int amtk_scan_create(amtk_ctx* ctx, int scanw, int scanh, int lx, int ly, int th
 
 void amtk_scan_destroy(amtk_scan* s) {
   if (!s) return;
-  { DevSelect ds(s->ctx); if (s->dSums) cudaFree(s->dSums); if (s->dBg) cudaFree(s->dBg); }
+  { DevSelect ds(s->device); if (s->dSums) cudaFree(s->dSums); if (s->dBg) cudaFree(s->dBg); }
   delete s;
 }
 

@@ -74,7 +74,9 @@ struct amtk_ctx {
 };
 
 struct amtk_logo {
-  amtk_ctx* ctx = nullptr;
+  // Device the HBM copies live on (-1 = none yet).  Deliberately NOT a pointer to the context that first evaluated the
+  // logo: logos are host objects that may outlive any context (use-after-free in destroy/ensure_device).
+  int device = -1;
   amtk::HostLogo host;
   // device copies (valid after create_mask; A/B valid from creation)
   float* dA = nullptr; float* dB = nullptr;       // Y planes
@@ -87,7 +89,8 @@ struct amtk_logo {
 };
 
 struct amtk_scan {
-  amtk_ctx* ctx = nullptr;
+  amtk_ctx* ctx = nullptr;                 // used by add_frames/get_* only (the context must be alive for those calls)
+  int device = 0;                          // amtk_scan_destroy needs nothing but the ordinal
   int scanw = 0, scanh = 0, logUVx = 1, logUVy = 1, thy = 0;
   int nvalid = 0;
   unsigned long long* dSums = nullptr;     // [npix][3] u64: sumF, sumF2, sumFB  (exact integers)

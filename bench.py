@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (BASELINE.json: "1920x1080i YV12 frames/sec (logo-eval + combing)").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (torchrun for N > 1)
     python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path on the host cores
+    python bench.py --config {comb_1440,logoscan_10k,logo_analyze,logo_scan}   # secondary BASELINE configs, one JSON line
 
 One step = one pass of the fused hot path (LogoFrame::ScanFrame logo evaluation, 1 logo, fades {0,1}, + the
 combing / field-difference counters) over ONE synthetic 1800-frame 1920x1080i YV12 clip (BASELINE.json configs[1]),
 resident in HBM (5.6 GB >> 126 MB L2, so no L2 flush is needed between steps).  N GPUs = N independent clips, one per
-rank (weak scaling), with one NCCL all-gather of the per-frame results per step.  Prints ONE JSON line on rank 0.
+rank (weak scaling), with ONE NCCL all-gather of the per-frame results per step, issued on a side stream.
+Prints ONE JSON line on rank 0.  The line carries a `parity` block: the WHOLE clip's GPU results compared with the
+reference's own code (logo scores, bitwise) and the combing spec (counters) -- a mismatch exits non-zero.
 """
 import argparse
 import json
@@ -26,6 +29,9 @@ IMGX, IMGY, LOGO_W, LOGO_H = 1700, 60, 64, 64
 MASKRATIO = 0.35
 SEED = 0x5EED0001
 METRIC = "1920x1080i YV12 frames/sec (logo-eval + combing)"
+WORKLOAD = "1920x1080i 1800-frame synthetic clip, AMTLogo eval every frame + combing (configs[1])"
+COMB_NOTE = ("combing half = this repo's spec in AVX2 (oracle/amtk_comb_avx2.c) -- NOT Amatsukaze code: the reference "
+             "has no implementation of it (external KFM plugin)")
 
 
 def measured_peak_gbs():
@@ -45,6 +51,21 @@ def staged_h2d_bytes(nframes, frame_bytes, budget=256 << 20):
         per -= 1
     chunks = (nframes + per - 1) // per
     return (nframes + chunks - 1) * frame_bytes
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs next to GPU `index` (NVML's ideal affinity) BEFORE any pinned host allocation, so
+    the staging memory of the end-to-end path sits on the GPU's own NUMA node (8-GPU e2e scaled 0.675 without it)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        return {"cpus": len(after), "cpus_before": before, "first": after[0], "last": after[-1]}
+    except Exception as e:      # no NVML / not permitted: run unbound
+        return {"error": str(e)[:80]}
 
 
 class ClockSampler(threading.Thread):
@@ -106,66 +127,192 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def make_clip(torch, synth, logo, device, seed, out=None):
-    """The 1800-frame synthetic clip, generated on the GPU in chunks (integer-only generator)."""
-    clip = torch.empty((CLIP_FRAMES, FRAME_BYTES), dtype=torch.uint8, device=device) if out is None else out
+def make_clip(torch, synth, logo, device, seed, w=W, h=H, nframes=CLIP_FRAMES, mode="interlaced", imgx=IMGX, imgy=IMGY, out=None):
+    """A synthetic clip generated on the GPU in chunks (integer-only generator, identical on CPU and CUDA)."""
+    fb = w * h * 3 // 2
+    clip = torch.empty((nframes, fb), dtype=torch.uint8, device=device) if out is None else out
     step = 20
-    for n0 in range(0, CLIP_FRAMES, step):
-        n = min(step, CLIP_FRAMES - n0)
-        synth.make_frames(n0, n, W, H, seed=seed, device=device, mode="interlaced", logo=logo, imgx=IMGX, imgy=IMGY,
-                          out=clip[n0:n0 + n])
+    for n0 in range(0, nframes, step):
+        n = min(step, nframes - n0)
+        synth.make_frames(n0, n, w, h, seed=seed, device=device, mode=mode, logo=logo, imgx=imgx, imgy=imgy, out=clip[n0:n0 + n])
     return clip
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_measure(po, frames, logo_data, th6, threads, passes=3, one_thread_frames=48):
+    """Times the CPU implementation on `frames` (numpy (n, FRAME_BYTES)): all usable threads (best of `passes`, plus the
+    logo-only and comb-only splits) and ONE thread -- how the reference really runs this path -- on a short prefix.
+    Returns (dict for cpu_baseline, scores, counts) with the results of the all-thread fused pass."""
+    n = frames.shape[0]
+    bN = po.CpuBench(W, H, logo_data, IMGX, IMGY, threads, MASKRATIO)
+    best, sc, cn = None, None, None
+    for _ in range(passes):
+        sec, sc, cn = bN.run(frames, th6, 3, "avx2")
+        best = sec if best is None else min(best, sec)
+    logo_sec = min(bN.run(frames, th6, 1, "avx2")[0] for _ in range(2))
+    comb_sec = min(bN.run(frames, th6, 2, "avx2")[0] for _ in range(2))
+    scal_n = min(n, max(threads, 16))
+    scal_sec = bN.run(frames[:scal_n], th6, 2, "scalar")[0]
+    kind = bN.kind
+    bN.close()
+    b1 = po.CpuBench(W, H, logo_data, IMGX, IMGY, 1, MASKRATIO)
+    n1 = min(n, one_thread_frames)
+    one = min(b1.run(frames[:n1], th6, 3, "avx2")[0] for _ in range(2))
+    one_logo = min(b1.run(frames[:n1], th6, 1, "avx2")[0] for _ in range(2))
+    b1.close()
+    info = {"value": n / best, "unit": "frames/s", "cores": threads, "threads": threads, "kind": kind,
+            "threads_N": n / best, "threads_1": n1 / one,
+            "logo_only": {"threads_N": n / logo_sec, "threads_1": n1 / one_logo, "code": "reference's own ComputeKernel.cpp/LogoScan.hpp (oracle/_ref)" if kind == "reference" else "C port (oracle/amtk_oracle.c)"},
+            "comb_only": {"threads_N": n / comb_sec, "threads_N_scalar_spec": scal_n / scal_sec, "code": "this repo's spec, AVX2 (not Amatsukaze code)"},
+            "host_cpus_online": os.cpu_count(),
+            "sample": "%d frames per pass (%.1f per thread), best of %d passes, thread team and scratch created outside the timed "
+                      "region; threads = affinity mask capped by the cgroup quota; logo half = %s; %s; 1-thread figure on %d frames"
+                      % (n, n / threads, passes, "reference's own code (oracle/_ref)" if kind == "reference" else "C port", COMB_NOTE, n1)}
+    return info, sc, cn
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU code (oracle/_ref) for the logo half + the scalar spec for the
-    combing half (absent from the reference), on all host cores, on a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU code (oracle/_ref) for the logo half + this repo's AVX2 comb spec for the
+    combing half (absent from the reference), on all usable host threads, on a bounded sample of the same workload."""
     if rank != 0:
         return
     import numpy as np
+    import torch
     from amatsukaze_b200 import synth
     from oracle import pyoracle as po
-    cores = os.cpu_count() or 1
-    sample = args.ref_frames
+    threads = po.usable_cpu_threads()
+    sample = args.ref_frames if args.ref_frames > 0 else max(96, min(CLIP_FRAMES, 8 * threads))
     logo = synth.make_logo(LOGO_W, LOGO_H)
-    frames = np.concatenate([synth.make_frames(CLIP_FRAMES // 3 + i, min(8, sample - i), W, H, seed=SEED, logo=logo,
-                                               imgx=IMGX, imgy=IMGY).numpy() for i in range(0, sample, 8)])
+    gen = "cpu"
+    if torch.cuda.is_available() and sample > 64:       # input generation only; the measured code runs on the host cores
+        gen = "cuda (input generation only)"
+        frames = make_clip(torch, synth, logo, "cuda", SEED, nframes=sample).cpu().numpy()
+    else:
+        uniq = min(sample, 64)                           # CPU generation is slow: tile a 64-frame unique set
+        base = np.concatenate([synth.make_frames(CLIP_FRAMES // 3 + i, min(8, uniq - i), W, H, seed=SEED, logo=logo,
+                                                 imgx=IMGX, imgy=IMGY).numpy() for i in range(0, uniq, 8)])
+        frames = np.concatenate([base] * ((sample + uniq - 1) // uniq))[:sample]
     th = [20, 12, 36, 24, 16, 48]
-    kind = "port"
+    b = po.CpuBench(W, H, logo["data"], IMGX, IMGY, threads, MASKRATIO)
     for _ in range(args.warmup):
-        _, _, _, kind = po.cpu_scan_comb(frames, W, H, logo["data"], IMGX, IMGY, th, cores, MASKRATIO)
-    total = 0.0
+        b.run(frames, th, 3, "avx2")
+    total, best = 0.0, None
     for _ in range(args.steps):
-        sec, sc, cn, kind = po.cpu_scan_comb(frames, W, H, logo["data"], IMGX, IMGY, th, cores, MASKRATIO)
+        sec = b.run(frames, th, 3, "avx2")[0]
         total += sec
+        best = sec if best is None else min(best, sec)
+    kind = b.kind
+    b.close()
+    b1 = po.CpuBench(W, H, logo["data"], IMGX, IMGY, 1, MASKRATIO)
+    n1 = min(sample, 48)
+    one = min(b1.run(frames[:n1], th, 3, "avx2")[0] for _ in range(2))
+    b1.close()
     fps = sample * args.steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
-        "config": {"workload": "1920x1080i 1800-frame synthetic clip, AMTLogo eval every frame + combing (configs[1])",
-                   "sample_frames_per_step": sample, "logo": "64x64 @(1700,60) maskratio 0.35"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": "%d consecutive 1920x1080 frames per step; logo half = %s, combing half = this repo's "
-                                   "scalar spec (not in the reference); OpenMP over frames" %
-                                   (sample, "reference's own ComputeKernel.cpp/LogoScan.hpp code (oracle/_ref)" if kind == "reference" else "C port (oracle/amtk_oracle.c)")},
+        "config": {"workload": WORKLOAD, "frames_per_step": sample, "logo": "64x64 @(1700,60) maskratio 0.35, fades {0,1}",
+                   "input_generated_on": gen},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "threads": threads, "kind": kind,
+                         "threads_N": fps, "threads_N_best_step": sample / best, "threads_1": n1 / one,
+                         "host_cpus_online": os.cpu_count(),
+                         "sample": "%d frames per step (%.1f per thread); threads = affinity mask capped by the cgroup quota; thread "
+                                   "team and scratch created outside the timed region; logo half = %s; %s"
+                                   % (sample, sample / threads,
+                                      "reference's own ComputeKernel.cpp/LogoScan.hpp code (oracle/_ref)" if kind == "reference" else "C port (oracle/amtk_oracle.c)",
+                                      COMB_NOTE)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# secondary BASELINE configs (device-resident, CUDA events on the context's stream)
+# ---------------------------------------------------------------------------------------------------------------
+def timed_ms(torch, stream, fn, reps):
+    fn()
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    stream.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def secondary_configs(torch, ab, synth, ctx, stream, device, which, peak):
+    """configs[2] (1440x1080 3600-field combing pass), configs[3] (LogoScan accumulation over 10000 1080p frames),
+    AMTAnalyzeLogo (33 evaluations per frame) and LogoFrame::ScanFrame alone, each device resident."""
+    out = {}
+    lg = synth.make_logo(LOGO_W, LOGO_H)
+    with torch.cuda.stream(stream):
+        if "comb_1440" in which:
+            w, h, n = 1440, 1080, 1800
+            t = make_clip(torch, synth, None, device, SEED, w, h, n, mode="telecine")
+            clip = ab.yv12_clip(t, w, h, n, True)
+            res = torch.empty((n, 12), dtype=torch.int32, device=device)
+            ms = timed_ms(torch, stream, lambda: ctx.comb_frames(clip, out=res), 20)
+            gbs = n * w * h * 1.5 / ms / 1e6
+            out["comb_1440"] = {"workload": "configs[2]: 1440x1080i 3600-field KFM combing/field-diff pass, 1800 frames resident",
+                                "ms": ms, "frames_per_s": n / ms * 1e3, "fields_per_s": 2 * n / ms * 1e3,
+                                "algorithmic_gbs": gbs, "frac_of_measured_hbm": gbs / peak}
+            del t, clip
+        if "logoscan_10k" in which:
+            w, h, n = 1920, 1080, 10000
+            t = make_clip(torch, synth, lg, device, SEED + 7, w, h, n, mode="flat")
+            clip = ab.yv12_clip(t, w, h, n, True)
+            for (sw, sh) in ((64, 64), (256, 128)):
+                acc = ctx.logo_scan(sw, sh, 12)
+                sx = IMGX if sw == 64 else 1600
+                ms = timed_ms(torch, stream, lambda: acc.add_frames(clip, sx, IMGY), 3)
+                out["logoscan_10k_%dx%d" % (sw, sh)] = {
+                    "workload": "configs[3]: LogoScan::AddFrame over 10000 resident 1920x1080 frames, ROI %dx%d, thy 12" % (sw, sh),
+                    "ms": ms, "frames_per_s": n / ms * 1e3, "roi_gbs": n * sw * sh * 1.5 / ms / 1e6,
+                    "note": "host-pointer validity output (10 kB D2H + sync) is inside the timing"}
+                del acc
+            del t, clip
+        if "logo_analyze" in which or "logo_scan" in which:
+            n = CLIP_FRAMES
+            t = make_clip(torch, synth, lg, device, SEED)
+            clip = ab.yv12_clip(t, W, H, n, True)
+            raw = ab.Logo.create(lg["data"], LOGO_W, LOGO_H, W, H, IMGX, IMGY)
+            de, top, bot = raw.deint().create_mask(MASKRATIO), raw.field(0).create_mask(MASKRATIO), raw.field(1).create_mask(MASKRATIO)
+            if "logo_scan" in which:
+                res = torch.empty((n, 1, 2), dtype=torch.float32, device=device)
+                ms = timed_ms(torch, stream, lambda: ctx.scan_frames(clip, [de], out=res), 20)
+                out["logo_scan"] = {"workload": "LogoFrame::ScanFrame alone (2 evaluations/frame), 1800 resident 1080p frames",
+                                    "ms": ms, "frames_per_s": n / ms * 1e3}
+            if "logo_analyze" in which:
+                res = torch.empty((n, 33), dtype=torch.float32, device=device)
+                ms = timed_ms(torch, stream, lambda: ctx.analyze_frames(clip, de, top, bot, out=res), 5)
+                out["logo_analyze"] = {"workload": "AMTAnalyzeLogo (33 evaluations/frame: deint + 2 field logos x 11 fades), 1800 resident 1080p frames",
+                                       "ms": ms, "frames_per_s": n / ms * 1e3, "evals_per_s": 33 * n / ms * 1e3}
+            del t, clip
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-frames", type=int, default=96, help="frames per step of the CPU reference arm (bounded sample)")
-    ap.add_argument("--cpu-frames", type=int, default=96, help="frames of the cpu_baseline leg of the default arm")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--config", default="headline",
+                    choices=["headline", "comb_1440", "logoscan_10k", "logo_analyze", "logo_scan", "secondary"])
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU reference arm (0 = 8 per thread, 96..1800)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline AND the full-clip parity check")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configs in the headline line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,6 +333,7 @@ def main():
     from amatsukaze_b200 import synth
 
     assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback)"
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else {"unbound": "single GPU run"}
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -193,6 +341,17 @@ def main():
 
     stream = torch.cuda.Stream(device=device)
     ctx = ab.Context(local_rank, stream.cuda_stream)
+    peak, peak_src = measured_peak_gbs()
+
+    if args.config != "headline":
+        which = ["comb_1440", "logoscan_10k", "logo_analyze", "logo_scan"] if args.config == "secondary" else [args.config]
+        res = secondary_configs(torch, ab, synth, ctx, stream, device, which, peak)
+        if rank == 0:
+            print(json.dumps({"config": args.config, "n_gpus": 1, "data": "synthetic", "timing": "CUDA events on the launch stream, device-resident inputs",
+                              "peak_gbs": peak, "results": res}), flush=True)
+        ctx.close()
+        return
+
     logo_def = synth.make_logo(LOGO_W, LOGO_H)
     logo = ab.Logo.create(logo_def["data"], LOGO_W, LOGO_H, W, H, IMGX, IMGY).deint().create_mask(MASKRATIO)
     prm = ab.default_comb_params()
@@ -206,19 +365,35 @@ def main():
     counts = results[CLIP_FRAMES * 2:].view(CLIP_FRAMES, 12)
     from amatsukaze_b200 import shard
     gathered = {}
+    # The score gather of a pass runs on its own stream: it waits (event) for the pass that produced `results`, copies
+    # them into a snapshot, and overlaps with the next pass instead of sitting between two passes on the compute stream.
+    gstream = torch.cuda.Stream(device=device) if world > 1 else None
+    snap = torch.empty_like(results) if world > 1 else None
+    ev_done = torch.cuda.Event() if world > 1 else None
+    ev_snap = torch.cuda.Event() if world > 1 else None
 
     def step():
+        if world > 1:
+            stream.wait_event(ev_snap)                    # previous snapshot taken before results are overwritten
         ctx.scan_comb_frames(clip, [logo], prm, scores=scores, counts=counts)
-        if world > 1:      # final score gather of the pass (NCCL over NVLink; ~100 KB per rank, no other traffic)
-            gathered["results"] = shard.gather_streams(results)
+        if world > 1:
+            ev_done.record(stream)
+            with torch.cuda.stream(gstream):
+                gstream.wait_event(ev_done)
+                snap.copy_(results, non_blocking=True)
+                ev_snap.record(gstream)
+                gathered["results"] = shard.gather_streams(snap)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     with torch.cuda.stream(stream):
+        if world > 1:
+            ev_snap.record(stream)
         for _ in range(max(args.warmup, 3)):
             step()
         stream.synchronize()
         if world > 1:
+            gstream.synchronize()
             dist.barrier()
         torch.cuda.synchronize()
         l0 = ctx.launches
@@ -229,6 +404,8 @@ def main():
         ev0.record(stream)
         for _ in range(args.steps):
             step()
+        if world > 1:
+            stream.wait_stream(gstream)                   # the last gather is part of the timed region
         ev1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -247,10 +424,12 @@ def main():
 
     # ---- end-to-end through the C ABI with HOST buffers: H2D of the clip + D2H of the results inside the timing ----
     e2e = None
-    if not args.no_e2e:
+    host = None
+    if not args.no_e2e or (rank == 0 and not args.no_cpu):
         host = torch.empty((CLIP_FRAMES, FRAME_BYTES), dtype=torch.uint8, pin_memory=True)
         host.copy_(clip_t)
         torch.cuda.synchronize()
+    if not args.no_e2e:
         hclip = ab.yv12_clip(host, W, H, CLIP_FRAMES, on_device=False)
         h_scores = np.empty((CLIP_FRAMES, 1, 2), np.float32)
         h_counts = np.empty((CLIP_FRAMES, 12), np.int32)
@@ -259,7 +438,6 @@ def main():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(args.e2e_steps):
@@ -275,17 +453,18 @@ def main():
         e2e = {"value": CLIP_FRAMES * world * args.e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": staged_h2d_bytes(CLIP_FRAMES, FRAME_BYTES),
                "d2h_bytes_per_step": int(h_scores.nbytes + h_counts.nbytes), "steps": args.e2e_steps,
-               "host_memory": "pinned", "matches_device_run": same}
-        del host
+               "host_memory": "pinned", "numa_binding": numa, "matches_device_run": same,
+               "h2d_gbs_per_gpu": staged_h2d_bytes(CLIP_FRAMES, FRAME_BYTES) * args.e2e_steps / (e2e_ms * 1e-3) / 1e9,
+               "note": "PCIe-bound by construction: every frame byte crosses the host link once"}
 
     # read-only ceiling on this GPU: a plain streaming reduction over the same 5.6 GB clip
     with torch.cuda.stream(stream):
         read_ceiling = ctx.probe_read_gbs(clip_t, reps=3)
 
     sampler.stop_flag = True
-    peak, peak_src = measured_peak_gbs()
+    exit_code = 0
     if rank == 0:
-        # roofline of the dominant kernel (comb_tma_kernel, 8-bit instantiation): algorithmic bytes = one read of every frame byte
+        # roofline of the dominant kernel: algorithmic bytes = one read of every frame byte
         alg_bytes = CLIP_FRAMES * FRAME_BYTES
         avg_ms = comb_ms / max(comb_n, 1)
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
@@ -296,44 +475,63 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        cpu = None
+        cpu, parity = None, None
         if not args.no_cpu:
+            # WHOLE-clip parity (outside every timed region) + the CPU baseline, on the host copy of the same clip
             from oracle import pyoracle as po
-            cores = os.cpu_count() or 1
-            nfr = args.cpu_frames
-            fr = clip_t[CLIP_FRAMES // 3: CLIP_FRAMES // 3 + nfr].cpu().numpy()
-            sec, sc, cn, kind = po.cpu_scan_comb(fr, W, H, logo_def["data"], IMGX, IMGY, prm.as_list(), cores, MASKRATIO)
-            # the frame before the sample differs from the oracle's "prev(0)=self", so compare from the 2nd frame on
-            g_sc = scores[CLIP_FRAMES // 3: CLIP_FRAMES // 3 + nfr, 0].cpu().numpy()
-            g_cn = counts[CLIP_FRAMES // 3: CLIP_FRAMES // 3 + nfr].cpu().numpy()
-            agree = bool(np.array_equal(g_sc.view(np.uint32), sc.view(np.uint32)) and np.array_equal(g_cn[1:], cn[1:]))
-            cpu = {"value": nfr / sec, "unit": "frames/s", "cores": cores, "kind": kind,
-                   "sample": "%d consecutive frames of the same clip; logo half = %s; combing half = this repo's scalar "
-                             "spec (not in the reference); OpenMP over frames; GPU results identical: %s"
-                             % (nfr, "reference's own code (oracle/_ref)" if kind == "reference" else "C port (oracle/amtk_oracle.c)", agree)}
+            threads = po.usable_cpu_threads()
+            fr = host.numpy()
+            cpu, sc, cn = cpu_measure(po, fr, logo_def["data"], prm.as_list(), threads)
+            g_sc = scores[:, 0].cpu().numpy()
+            g_cn = counts.cpu().numpy()
+            s_ok = bool(np.array_equal(g_sc.view(np.uint32), sc.view(np.uint32)))
+            c_ok = bool(np.array_equal(g_cn, cn))
+            # the scalar (normative) form of the combing spec on a prefix, as a second witness next to the AVX2 one
+            nsc = 48
+            b = po.CpuBench(W, H, logo_def["data"], IMGX, IMGY, threads, MASKRATIO)
+            _, _, cn_s = b.run(fr[:nsc], prm.as_list(), 2, "scalar")
+            b.close()
+            c_ok_scalar = bool(np.array_equal(g_cn[:nsc], cn_s))
+            parity = {"frames": CLIP_FRAMES, "scores_bitexact": s_ok, "counts_equal": c_ok and c_ok_scalar,
+                      "oracle": cpu["kind"], "scores_checked_against": "reference's own code (oracle/_ref), float bit patterns" if cpu["kind"] == "reference" else "C port of the reference",
+                      "counts_checked_against": "combing spec: AVX2 form on all %d frames (frame 0 with prev = itself), scalar normative form on the first %d" % (CLIP_FRAMES, nsc),
+                      "score_mismatches": int((g_sc.view(np.uint32) != sc.view(np.uint32)).any(axis=1).sum()),
+                      "count_mismatches": int((g_cn != cn).any(axis=1).sum())}
+            if not (s_ok and c_ok and c_ok_scalar):
+                exit_code = 3
+        secondary = None
+        if not args.no_secondary and world == 1:
+            del clip_t
+            torch.cuda.empty_cache()
+            secondary = secondary_configs(torch, ab, synth, ctx, stream, device, ["comb_1440", "logoscan_10k", "logo_analyze", "logo_scan"], peak)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
-            "config": {"workload": "1920x1080i 1800-frame synthetic clip, AMTLogo eval every frame + combing (configs[1])",
+            "config": {"workload": WORKLOAD,
                        "frames_per_step_per_gpu": CLIP_FRAMES, "logo": "64x64 @(1700,60) maskratio 0.35, fades {0,1}",
                        "l2": "step input 5.6 GB per GPU is larger than the 126 MB L2 (no flush needed)",
-                       "parallelism": "one independent clip per GPU" + ("; NCCL all_gather of results per step" if world > 1 else "")},
+                       "parallelism": "one independent clip per GPU" + ("; one NCCL all_gather of the results per step on a side stream" if world > 1 else "")},
             "clocks": sampler.summary(),
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "comb_tma_kernel<CombCfg<17,8,3,0,8>,1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "comb_tma_kernel (8-bit streaming pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": int(comb_n),
                          "share_of_step": (comb_ms / max(elapsed_ms, 1e-9)),
                          "read_only_ceiling_gbs": read_ceiling},
             "cpu_baseline": cpu,
+            "parity": parity,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+    if exit_code:
+        sys.stderr.write("bench.py: PARITY MISMATCH against the CPU oracle (see the `parity` block)\n")
+        sys.exit(exit_code)
 
 
 if __name__ == "__main__":

@@ -544,17 +544,36 @@ void amtk_or_comb_frame_u16(const uint16_t* curY, const uint16_t* curU, const ui
  * ---------------------------------------------------------------------------------------------- */
 static double now_sec(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
-double amtk_or_bench_scan_comb_u8(const amtk_or_logo* lg, const uint8_t* frames, int nframes,
-                                  int w, int h, const int* th6, int nthreads, float* out_scores, int32_t* out_counts) {
+void amtk_or_comb_frame_u8_avx2(const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                                int, int, int, int, int, int, const int*, int32_t*);   /* oracle/amtk_comb_avx2.c */
+
+/* mode: bit 0 = logo ScanFrame, bit 1 = combing counters; comb_impl: 0 scalar spec, 1 AVX2 spec.  The thread team is
+ * spun up before the clock starts. */
+double amtk_or_bench_run(const amtk_or_logo* lg, const uint8_t* frames, int nframes, int w, int h, const int* th6,
+                         int nthreads, int mode, int comb_impl, float* out_scores, int32_t* out_counts) {
   size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2), fsz = ysz + 2 * csz;
+  volatile int sink = 0;
+#pragma omp parallel num_threads(nthreads)
+  { sink += 1; }
   double t0 = now_sec();
 #pragma omp parallel for num_threads(nthreads) schedule(static)
   for (int n = 0; n < nframes; ++n) {
     const uint8_t* cur = frames + (size_t)n * fsz;
     const uint8_t* prev = frames + (size_t)(n > 0 ? n - 1 : 0) * fsz;
-    amtk_or_scan_frame_u8(lg, cur, w, 255.0f, out_scores + (size_t)n * 2);
-    amtk_or_comb_frame_u8(cur, cur + ysz, cur + ysz + csz, prev, prev + ysz, prev + ysz + csz,
-                          w, h, w, w / 2, 1, 1, th6, out_counts + (size_t)n * 12);
+    if (mode & 1) amtk_or_scan_frame_u8(lg, cur, w, 255.0f, out_scores + (size_t)n * 2);
+    if (mode & 2) {
+      if (comb_impl == 1)
+        amtk_or_comb_frame_u8_avx2(cur, cur + ysz, cur + ysz + csz, prev, prev + ysz, prev + ysz + csz,
+                                   w, h, w, w / 2, 1, 1, th6, out_counts + (size_t)n * 12);
+      else
+        amtk_or_comb_frame_u8(cur, cur + ysz, cur + ysz + csz, prev, prev + ysz, prev + ysz + csz,
+                              w, h, w, w / 2, 1, 1, th6, out_counts + (size_t)n * 12);
+    }
   }
   return now_sec() - t0;
+}
+
+double amtk_or_bench_scan_comb_u8(const amtk_or_logo* lg, const uint8_t* frames, int nframes,
+                                  int w, int h, const int* th6, int nthreads, float* out_scores, int32_t* out_counts) {
+  return amtk_or_bench_run(lg, frames, nframes, w, h, th6, nthreads, 3, 0, out_scores, out_counts);
 }

@@ -109,6 +109,14 @@ void amtk_or_comb_frame_u16(const uint16_t* curY, const uint16_t* curU, const ui
 /* Bounded CPU-baseline loops used by bench.py (port leg): returns seconds of wall time. */
 double amtk_or_bench_scan_comb_u8(const amtk_or_logo* deint_logo, const uint8_t* frames, int nframes,
                                   int w, int h, const int* th6, int nthreads, float* out_scores, int32_t* out_counts);
+/* mode: bit 0 = logo ScanFrame, bit 1 = combing counters; comb_impl: 0 = scalar spec, 1 = AVX2 spec (amtk_comb_avx2.c) */
+double amtk_or_bench_run(const amtk_or_logo* deint_logo, const uint8_t* frames, int nframes, int w, int h, const int* th6,
+                         int nthreads, int mode, int comb_impl, float* out_scores, int32_t* out_counts);
+/* AVX2 form of the combing spec (oracle/amtk_comb_avx2.c; NOT Amatsukaze code); same contract as amtk_or_comb_frame_u8 */
+void amtk_or_comb_frame_u8_avx2(const uint8_t* curY, const uint8_t* curU, const uint8_t* curV,
+                                const uint8_t* prevY, const uint8_t* prevU, const uint8_t* prevV,
+                                int w, int h, int pitchY, int pitchUV, int logUVx, int logUVy, const int* th6, int32_t* counts12);
+int amtk_or_comb_have_avx2(void);
 
 #ifdef __cplusplus
 }

@@ -28,12 +28,16 @@ def build_oracle(force=False):
     """Compile oracle/amtk_oracle.c (gcc, no contraction, no fast-math)."""
     src = os.path.join(HERE, "amtk_oracle.c")
     hdr = os.path.join(HERE, "amtk_oracle.h")
+    avx = os.path.join(HERE, "amtk_comb_avx2.c")
     if (not force and os.path.exists(ORACLE_SO)
-            and os.path.getmtime(ORACLE_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(ORACLE_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(avx))):
         return ORACLE_SO
     os.makedirs(os.path.dirname(ORACLE_SO), exist_ok=True)
+    obj = os.path.join(os.path.dirname(ORACLE_SO), "amtk_comb_avx2.o")
+    # the AVX2 form of the combing spec is its own object so that -mavx2 never touches the float restatement
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-fPIC", "-mavx2", "-c", avx, "-o", obj])
     cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
-           "-o", ORACLE_SO, src, "-lm"]
+           "-o", ORACLE_SO, src, obj, "-lm"]
     subprocess.check_call(cmd)
     return ORACLE_SO
 
@@ -41,7 +45,9 @@ def build_oracle(force=False):
 def build_ref():
     """Run oracle/build_ref.sh when the reference tree is present (this container only)."""
     if os.path.exists("/root/reference/Amatsukaze/ComputeKernel.cpp"):
-        subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
+        srcs = [os.path.join(HERE, f) for f in ("build_ref.sh", "ref_glue.cpp", "amtk_oracle.c", "amtk_comb_avx2.c", "shim/ref_shim.h")]
+        if not os.path.exists(REF_SO) or os.path.getmtime(REF_SO) < max(os.path.getmtime(f) for f in srcs):
+            subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
     return REF_SO if os.path.exists(REF_SO) else None
 
 
@@ -124,6 +130,11 @@ def oracle_lib():
         L.amtk_or_scan_add_frame_u8.argtypes = [SP, c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int]
         L.amtk_or_scan_get_logo.restype = C.c_int
         L.amtk_or_scan_get_logo.argtypes = [SP, C.c_int, C.c_int, c_float_p]
+        L.amtk_or_comb_frame_u8_avx2.restype = None
+        L.amtk_or_comb_frame_u8_avx2.argtypes = [c_u8_p] * 6 + [C.c_int] * 6 + [c_i32_p, c_i32_p]
+        L.amtk_or_comb_have_avx2.restype = C.c_int
+        L.amtk_or_bench_run.restype = C.c_double
+        L.amtk_or_bench_run.argtypes = [LP, c_u8_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int, C.c_int, C.c_int, c_float_p, c_i32_p]
         L.amtk_or_bench_scan_comb_u8.restype = C.c_double
         L.amtk_or_bench_scan_comb_u8.argtypes = [LP, c_u8_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int, c_float_p, c_i32_p]
         _oracle = L
@@ -218,8 +229,9 @@ def or_analyze_frame(dl, ft, fb, planeY, maxv=None, pitch=None):
     return out
 
 
-def or_comb_frame(cur, prev, th6):
-    """cur/prev = (Y,U,V) arrays (2-D, contiguous rows = pitch).  Returns int32[12]."""
+def or_comb_frame(cur, prev, th6, impl="scalar"):
+    """cur/prev = (Y,U,V) arrays (2-D, contiguous rows = pitch).  Returns int32[12].
+    impl: "scalar" = the normative spec loop, "avx2" = its vectorised form (8-bit only)."""
     L = oracle_lib()
     cy, cu, cv = [np.ascontiguousarray(p) for p in cur]
     py, pu, pv = [np.ascontiguousarray(p) for p in prev]
@@ -230,7 +242,7 @@ def or_comb_frame(cur, prev, th6):
     out = np.zeros(12, np.int32)
     if cy.dtype == np.uint8:
         t = c_u8_p
-        fn = L.amtk_or_comb_frame_u8
+        fn = L.amtk_or_comb_frame_u8_avx2 if impl == "avx2" else L.amtk_or_comb_frame_u8
     else:
         t = c_u16_p
         fn = L.amtk_or_comb_frame_u16
@@ -388,6 +400,11 @@ def ref_lib():
         R.ref_scan_get_logo.argtypes = [V, C.c_int, c_float_p]
         R.ref_logoframe_write.restype = C.c_int
         R.ref_logoframe_write.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int), c_float_p]
+        R.ref_bench_create.restype = V
+        R.ref_bench_create.argtypes = [V, C.c_int, C.c_int, C.c_int]
+        R.ref_bench_free.argtypes = [V]
+        R.ref_bench_run.restype = C.c_double
+        R.ref_bench_run.argtypes = [V, c_u8_p, C.c_int, c_i32_p, C.c_int, C.c_int, c_float_p, c_i32_p]
         R.ref_bench_scan_comb_u8.restype = C.c_double
         R.ref_bench_scan_comb_u8.argtypes = [V, c_u8_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int, c_float_p, c_i32_p]
         _ref = R
@@ -406,24 +423,81 @@ def ref_logoframe(eval_results, frames_per_sec, outpath=None, num_candidates=-1)
     return best.value, ratio.value
 
 
-def cpu_scan_comb(frames, w, h, logo_data, imgx, imgy, th6, nthreads, maskratio=0.35, logo_w=64, logo_h=64):
-    """Bounded CPU run of the fused hot path (ScanFrame + comb) over packed-YV12 `frames` (numpy uint8 (n, w*h*3/2)).
-    Uses the reference's own compiled code for the logo half when oracle/_ref exists ("reference"), else the
-    plain-C port ("port").  Returns (seconds, scores (n,2), counts (n,12), kind)."""
-    fr = np.ascontiguousarray(frames, np.uint8)
-    n = fr.shape[0]
-    scores = np.zeros((n, 2), np.float32)
-    counts = np.zeros((n, 12), np.int32)
-    th = np.asarray(th6, np.int32)
-    if ref_available():
-        lg = RefLogo.create(logo_data, logo_w, logo_h, w, h, imgx, imgy).deint().create_mask(maskratio)
-        sec = ref_lib().ref_bench_scan_comb_u8(lg.ptr, _p(fr, c_u8_p), n, w, h, _p(th, c_i32_p), nthreads,
-                                               _p(scores, c_float_p), _p(counts, c_i32_p))
-        return sec, scores, counts, "reference"
-    lg = OracleLogo.create(logo_data, logo_w, logo_h, w, h, imgx, imgy).deint().create_mask(maskratio)
-    sec = oracle_lib().amtk_or_bench_scan_comb_u8(lg.ptr, _p(fr, c_u8_p), n, w, h, _p(th, c_i32_p), nthreads,
-                                                  _p(scores, c_float_p), _p(counts, c_i32_p))
-    return sec, scores, counts, "port"
+def usable_cpu_threads():
+    """Host threads this process may really use: the affinity mask capped by the cgroup CPU quota (os.cpu_count()
+    ignores both, which oversubscribed the round-1 CPU arm)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", ):
+        try:
+            quota, period = open(path).read().split()[:2]
+            if quota != "max":
+                n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+        except Exception:
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and per > 0:
+            n = min(n, max(1, int(q / per + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+class CpuBench:
+    """Bounded CPU runs of the fused hot path (ScanFrame + comb) over packed-YV12 frames (numpy uint8 (n, w*h*3/2)).
+    Logo half: the reference's own compiled code when oracle/_ref exists (kind "reference"), else the plain-C port
+    ("port").  Combing half: this repo's spec, scalar or AVX2 (comb_impl) -- not Amatsukaze code either way.
+    The thread team and all scratch are created here, outside any timed region."""
+
+    def __init__(self, w, h, logo_data, imgx, imgy, nthreads, maskratio=0.35, logo_w=64, logo_h=64):
+        self.w, self.h, self.nthreads = w, h, int(nthreads)
+        self.kind = "reference" if ref_available() else "port"
+        if self.kind == "reference":
+            self.logo = RefLogo.create(logo_data, logo_w, logo_h, w, h, imgx, imgy).deint().create_mask(maskratio)
+            self.hb = C.c_void_p(ref_lib().ref_bench_create(self.logo.ptr, w, h, self.nthreads))
+        else:
+            self.logo = OracleLogo.create(logo_data, logo_w, logo_h, w, h, imgx, imgy).deint().create_mask(maskratio)
+            self.hb = None
+        self.comb_avx2 = bool(oracle_lib().amtk_or_comb_have_avx2())
+
+    def close(self):
+        if self.hb:
+            ref_lib().ref_bench_free(self.hb)
+            self.hb = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, frames, th6, mode=3, comb_impl="avx2"):
+        """One pass.  mode: 1 logo only, 2 comb only, 3 both.  Returns (seconds, scores (n,2), counts (n,12))."""
+        fr = frames if (isinstance(frames, np.ndarray) and frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]) \
+            else np.ascontiguousarray(frames, np.uint8)
+        n = fr.shape[0]
+        scores = np.zeros((n, 2), np.float32)
+        counts = np.zeros((n, 12), np.int32)
+        th = np.asarray(th6, np.int32)
+        ci = 1 if comb_impl == "avx2" else 0
+        if self.kind == "reference":
+            sec = ref_lib().ref_bench_run(self.hb, _p(fr, c_u8_p), n, _p(th, c_i32_p), mode, ci, _p(scores, c_float_p), _p(counts, c_i32_p))
+        else:
+            sec = oracle_lib().amtk_or_bench_run(self.logo.ptr, _p(fr, c_u8_p), n, self.w, self.h, _p(th, c_i32_p), self.nthreads,
+                                                 mode, ci, _p(scores, c_float_p), _p(counts, c_i32_p))
+        return sec, scores, counts
+
+
+def cpu_scan_comb(frames, w, h, logo_data, imgx, imgy, th6, nthreads, maskratio=0.35, logo_w=64, logo_h=64, comb_impl="scalar"):
+    """One-shot form: returns (seconds, scores (n,2), counts (n,12), kind)."""
+    b = CpuBench(w, h, logo_data, imgx, imgy, nthreads, maskratio, logo_w, logo_h)
+    sec, scores, counts = b.run(frames, th6, 3, comb_impl)
+    b.close()
+    return sec, scores, counts, b.kind
 
 
 class RefLogo:

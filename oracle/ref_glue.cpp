@@ -182,42 +182,88 @@ int ref_logoframe_write(const float* eval /* [numFrames][numLogos][2] */, int nu
   } catch (const IOException&) { return 0; }
 }
 
-/* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline leg) ----------------------------
+/* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline / parity legs) ---------------------
  * Per frame: LogoFrame::ScanFrame (LogoScan.hpp:1559-1566) with the reference's OWN DeintY + EvaluateLogo
  * (incl. CalcCorrelation5x5_AVX), followed by the combing metric, which the reference does not contain and is
- * therefore this repo's scalar spec (amtk_or_comb_frame_u8, linked in from oracle/amtk_oracle.c).
- * frames: packed YV12.  OpenMP over independent frames; each thread owns a private LogoDataParam clone because
- * EvaluateLogo is only re-entrant across distinct scratch buffers.  Returns wall seconds. */
+ * therefore this repo's spec -- scalar (amtk_or_comb_frame_u8) or its AVX2 form (amtk_or_comb_frame_u8_avx2), both
+ * linked in from oracle/.  frames: packed YV12.  OpenMP over independent frames.
+ *
+ * A bench handle owns the thread team and every per-thread scratch buffer, so the timed region (ref_bench_run)
+ * contains no thread creation and no allocation.  EvaluateLogo only writes its `work` argument,
+ * so all threads share the one LogoDataParam. */
 void amtk_or_comb_frame_u8(const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
                            int, int, int, int, int, int, const int*, int32_t*);
+void amtk_or_comb_frame_u8_avx2(const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                                int, int, int, int, int, int, const int*, int32_t*);
 }
 #include <time.h>
 #include <omp.h>
+struct RefBench {
+  LogoDataParam* lg; int w, h, nthreads;
+  std::vector<std::vector<float>> deint, work;
+};
 extern "C" {
-double ref_bench_scan_comb_u8(void* deint_logo, const uint8_t* frames, int nframes, int w, int h, const int* th6,
-                              int nthreads, float* out_scores, int32_t* out_counts) {
-  LogoDataParam* lg = (LogoDataParam*)deint_logo;
+void* ref_bench_create(void* deint_logo, int w, int h, int nthreads) {
+  RefBench* b = new RefBench();
+  b->lg = (LogoDataParam*)deint_logo; b->w = w; b->h = h; b->nthreads = nthreads < 1 ? 1 : nthreads;
+  b->deint.resize(b->nthreads); b->work.resize(b->nthreads);
+  const size_t n = (size_t)b->lg->w * b->lg->h + 8;
+  volatile int sink = 0;
+#pragma omp parallel num_threads(b->nthreads)
+  {   /* spins the team up and makes every thread touch its own scratch (first-touch placement) */
+    const int t = omp_get_thread_num();
+    b->deint[t].assign(n, 0.0f); b->work[t].assign(n, 0.0f);
+    sink += (int)b->deint[t][0];
+  }
+  return b;
+}
+void ref_bench_free(void* p) { delete (RefBench*)p; }
+int ref_bench_threads(void* p) { return ((RefBench*)p)->nthreads; }
+/* mode: bit 0 = logo ScanFrame (reference code), bit 1 = combing counters; comb_impl: 0 scalar spec, 1 AVX2 spec.
+ * Returns wall seconds of one pass over nframes frames. */
+double ref_bench_run(void* p, const uint8_t* frames, int nframes, const int* th6, int mode, int comb_impl,
+                     float* out_scores, int32_t* out_counts) {
+  RefBench* b = (RefBench*)p;
+  LogoDataParam* lg = b->lg;
+  const int w = b->w, h = b->h;
   const size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2), fsz = ysz + 2 * csz;
-  const int n = lg->w * lg->h;
+  const int off = lg->imgx + lg->imgy * w;
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
-#pragma omp parallel num_threads(nthreads)
+#pragma omp parallel num_threads(b->nthreads)
   {
-    std::vector<float> deint((size_t)n + 8), work((size_t)n + 8);
+    const int t = omp_get_thread_num();
+    float* deint = b->deint[t].data(); float* work = b->work[t].data();
 #pragma omp for schedule(static)
     for (int i = 0; i < nframes; ++i) {
       const uint8_t* cur = frames + (size_t)i * fsz;
       const uint8_t* prev = frames + (size_t)(i > 0 ? i - 1 : 0) * fsz;
-      int off = lg->imgx + lg->imgy * w;
-      DeintY<uint8_t>(deint.data(), cur + off, w, lg->w, lg->h);
-      out_scores[(size_t)i * 2 + 0] = lg->EvaluateLogo(deint.data(), 255.0f, 0, work.data());
-      out_scores[(size_t)i * 2 + 1] = lg->EvaluateLogo(deint.data(), 255.0f, 1, work.data());
-      amtk_or_comb_frame_u8(cur, cur + ysz, cur + ysz + csz, prev, prev + ysz, prev + ysz + csz,
-                            w, h, w, w / 2, 1, 1, th6, out_counts + (size_t)i * 12);
+      if (mode & 1) {
+        DeintY<uint8_t>(deint, cur + off, w, lg->w, lg->h);
+        out_scores[(size_t)i * 2 + 0] = lg->EvaluateLogo(deint, 255.0f, 0, work);
+        out_scores[(size_t)i * 2 + 1] = lg->EvaluateLogo(deint, 255.0f, 1, work);
+      }
+      if (mode & 2) {
+        if (comb_impl == 1)
+          amtk_or_comb_frame_u8_avx2(cur, cur + ysz, cur + ysz + csz, prev, prev + ysz, prev + ysz + csz,
+                                     w, h, w, w / 2, 1, 1, th6, out_counts + (size_t)i * 12);
+        else
+          amtk_or_comb_frame_u8(cur, cur + ysz, cur + ysz + csz, prev, prev + ysz, prev + ysz + csz,
+                                w, h, w, w / 2, 1, 1, th6, out_counts + (size_t)i * 12);
+      }
     }
   }
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* one-shot form kept for older callers: create + run + free (allocation and team start-up are NOT timed) */
+double ref_bench_scan_comb_u8(void* deint_logo, const uint8_t* frames, int nframes, int w, int h, const int* th6,
+                              int nthreads, float* out_scores, int32_t* out_counts) {
+  void* b = ref_bench_create(deint_logo, w, h, nthreads);
+  const double s = ref_bench_run(b, frames, nframes, th6, 3, 0, out_scores, out_counts);
+  ref_bench_free(b);
+  return s;
 }
 
 } /* extern "C" */

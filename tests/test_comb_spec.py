@@ -84,3 +84,36 @@ def test_first_frame_compares_with_itself_and_fields_partition_rows():
     # thresholds of 1 count every pixel with a non-zero response: top + bottom rows = H-4 rows of luma
     all1 = po.or_comb_clip(Y, U, V, [1, 1, 1, 1, 1, 1])
     assert np.all(all1[:, 1] + all1[:, 4] <= (H - 4) * W)
+
+
+def test_avx2_form_equals_scalar_spec():
+    """oracle/amtk_comb_avx2.c (the vectorised CPU baseline of bench.py; NOT Amatsukaze code) against the scalar
+    normative spec and the numpy restatement: ragged widths (vector tails), tiny planes, extreme thresholds."""
+    rng = np.random.default_rng(11)
+    shapes = ((1920, 1080), (1440, 1080), (352, 270), (96, 36), (50, 22), (34, 6), (16, 4), (70, 10))
+    ths = ([20, 12, 36, 24, 16, 48], [1, 1, 1, 1, 1, 1], [128, 2047, 300, 255, 1530, 1531], [0, 0, -5, 300, 40000, 70000],
+           [255, 1, 1530, 256, 2, 3])
+    for (W, H) in shapes:
+        cur = [rng.integers(0, 256, (H >> s, W >> s), dtype=np.int64).astype(np.uint8) for s in (0, 1, 1)]
+        # previous frame: mostly close to the current one so that the move threshold splits the pixels
+        prv = [np.clip(c.astype(np.int64) + rng.integers(-40, 41, c.shape), 0, 255).astype(np.uint8) for c in cur]
+        for th6 in ths:
+            a = po.or_comb_frame(tuple(cur), tuple(prv), th6)
+            b = po.or_comb_frame(tuple(cur), tuple(prv), th6, "avx2")
+            assert np.array_equal(a, b), (W, H, th6, a, b)
+        if W <= 352:
+            assert np.array_equal(np.asarray(po.or_comb_frame(tuple(cur), tuple(prv), ths[0], "avx2"), np.int32),
+                                  numpy_spec(cur, prv, ths[0]))
+    # saturated input: every comb response at its maximum
+    H, W = 40, 64
+    stripes = np.zeros((H, W), np.uint8); stripes[0::2] = 255
+    cur = [stripes, stripes[:H // 2, :W // 2].copy(), stripes[:H // 2, :W // 2].copy()]
+    prv = [255 - c for c in cur]
+    for th6 in ([255, 1530, 1530, 255, 1530, 1530], [255, 1531, 1531, 255, 1531, 1531]):
+        assert np.array_equal(po.or_comb_frame(tuple(cur), tuple(prv), th6), po.or_comb_frame(tuple(cur), tuple(prv), th6, "avx2"))
+
+
+def test_usable_cpu_threads_respects_affinity():
+    import os
+    n = po.usable_cpu_threads()
+    assert 1 <= n <= len(os.sched_getaffinity(0))

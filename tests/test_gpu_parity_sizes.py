@@ -1,0 +1,164 @@
+"""GPU parity at BASELINE.json's own sizes: configs[2] geometry (1440x1080: 11.25 luma
+tiles, a quarter-used last tile column, 5.625 chroma tiles), 8- and 10-bit, against the spec oracle; configs[3]
+(LogoScan accumulation over 10000 1920x1080 frames, ROI 64x64 and 256x128) against the reference's own LogoScan code
+(oracle/_ref) where it exists, else the C port; a whole 1080p clip against the reference-compiled logo code.  Everything
+goes through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import amatsukaze_b200 as ab
+from amatsukaze_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _gen(n0, n, w, h, **kw):
+    out = torch.empty((n, w * h * 3 // 2), dtype=torch.uint8, device="cuda")
+    for k in range(0, n, 10):
+        m = min(10, n - k)
+        synth.make_frames(n0 + k, m, w, h, device="cuda", out=out[k:k + m], **kw)
+    return out
+
+
+@pytest.mark.timeout(900)
+def test_comb_1440x1080_8bit_and_10bit(ctx, oracle):
+    po = oracle
+    w, h, n = 1440, 1080, 18
+    prm = ab.default_comb_params()
+    f8 = _gen(3, n, w, h, mode="telecine")
+    got = ctx.comb_frames(ab.yv12_clip(f8, w, h, n, True), prm).cpu().numpy()
+    Y, U, V = synth.split_planes(f8, w, h)
+    ref = np.stack([po.or_comb_frame((Y[i], U[i], V[i]), (Y[max(i - 1, 0)], U[max(i - 1, 0)], V[max(i - 1, 0)]), prm.as_list(), "avx2")
+                    for i in range(n)])
+    assert np.array_equal(got, ref), np.argwhere(got != ref)[:5]
+    # the scalar normative form on a few frames (AVX2 == scalar is a CPU test; this is the direct witness)
+    for i in (0, 1, 9, 17):
+        j = max(i - 1, 0)
+        assert np.array_equal(got[i], po.or_comb_frame((Y[i], U[i], V[i]), (Y[j], U[j], V[j]), prm.as_list()))
+    assert ref[:, [1, 4]].sum() > 0 and ref[1:, 0].sum() > 0
+    # range calls with a halo frame give the same rows
+    part = np.concatenate([ctx.comb_frames(ab.yv12_clip(f8, w, h, n, True), prm, 0, 7).cpu().numpy(),
+                           ctx.comb_frames(ab.yv12_clip(f8, w, h, n, True), prm, 7, n - 7).cpu().numpy()])
+    assert np.array_equal(part, ref)
+    # YUV420P10: same geometry, 16-bit samples (fp32 stencil path)
+    n10 = 16
+    f16 = (f8[:n10].to(torch.int32) * 4 + (f8[:n10].to(torch.int32) & 3)).to(torch.int16).contiguous()
+    p10 = ab.default_comb_params()
+    p10.th_move_y, p10.th_shima_y, p10.th_lshima_y = 80, 48, 144
+    p10.th_move_c, p10.th_shima_c, p10.th_lshima_c = 96, 64, 192
+    got10 = ctx.comb_frames(ab.yv12_clip(f16, w, h, n10, True, bits=10), p10).cpu().numpy()
+    a16 = f16.cpu().numpy().view(np.uint16)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    Y = a16[:, :ysz].reshape(n10, h, w); U = a16[:, ysz:ysz + csz].reshape(n10, h // 2, w // 2); V = a16[:, ysz + csz:].reshape(n10, h // 2, w // 2)
+    ref10 = po.or_comb_clip(Y, U, V, p10.as_list())
+    assert np.array_equal(got10, ref10) and ref10[:, 1].sum() > 0
+
+
+@pytest.mark.timeout(900)
+def test_scan_and_analyze_1440x1080(ctx, oracle):
+    """configs[0]'s geometry (1440x1080, 64x64 template at (1280, 64)) on the GPU, against the reference's own code."""
+    po = oracle
+    w, h, n, imgx, imgy = 1440, 1080, 16, 1280, 64
+    lg = synth.make_logo(64, 64)
+    fr = _gen(35, n, w, h, logo=lg, imgx=imgx, imgy=imgy, logo_period=16)
+    raw = ab.Logo.create(lg["data"], 64, 64, w, h, imgx, imgy)
+    de, top, bot = raw.deint().create_mask(0.35), raw.field(0).create_mask(0.35), raw.field(1).create_mask(0.35)
+    clip = ab.yv12_clip(fr, w, h, n, True)
+    s = ctx.scan_frames(clip, [de]).cpu().numpy()
+    a = ctx.analyze_frames(clip, de, top, bot).cpu().numpy()
+    Y, _, _ = synth.split_planes(fr, w, h)
+    if po.ref_available():
+        r = po.RefLogo.create(lg["data"], 64, 64, w, h, imgx, imgy)
+        rde, rtop, rbot = r.deint().create_mask(0.35), r.field(0).create_mask(0.35), r.field(1).create_mask(0.35)
+        rs = np.stack([po.ref_scan_frame(rde, Y[i]) for i in range(n)])
+        ra = np.stack([po.ref_analyze_frame(rde, rtop, rbot, Y[i]) for i in range(0, n, 5)])
+    else:
+        o = po.OracleLogo.create(lg["data"], 64, 64, w, h, imgx, imgy)
+        ode, otop, obot = o.deint().create_mask(0.35), o.field(0).create_mask(0.35), o.field(1).create_mask(0.35)
+        rs = np.stack([ode.scan_frame(Y[i]) for i in range(n)])
+        ra = np.stack([po.or_analyze_frame(ode, otop, obot, Y[i]) for i in range(0, n, 5)])
+    assert np.array_equal(_bits(s[:, 0]), _bits(rs))
+    assert np.array_equal(_bits(a[0:n:5]), _bits(ra))
+    assert rs[:, 0].max() > 0.5 and rs[:, 0].min() < 0.2
+
+
+@pytest.mark.timeout(1800)
+def test_logoscan_10000_frames_1080p(ctx, oracle):
+    """configs[3]: 10000 resident 1920x1080 frames (31 GB), ROI 64x64 and 256x128: u64 sums, gridDim.y frame splits,
+    validity per frame, and the derived logo (A/B planes) -- all exact."""
+    po = oracle
+    w, h, n = 1920, 1080, 10000
+    free, _ = torch.cuda.mem_get_info()
+    if free < 36 * (1 << 30):
+        pytest.skip("needs 36 GB of free HBM")
+    lg = synth.make_logo(64, 64)
+    fr = torch.empty((n, w * h * 3 // 2), dtype=torch.uint8, device="cuda")
+    for k in range(0, n, 20):
+        synth.make_frames(k, 20, w, h, seed=0x5EED0007, device="cuda", mode="flat", logo=lg, imgx=1700, imgy=60, out=fr[k:k + 20])
+    clip = ab.yv12_clip(fr, w, h, n, True)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    for (sx, sy, sw, sh) in ((1700, 60, 64, 64), (1600, 60, 256, 128)):
+        acc = ctx.logo_scan(sw, sh, 12)
+        valid = acc.add_frames(clip, sx, sy, 0, 6000)
+        valid = np.concatenate([valid, acc.add_frames(clip, sx, sy, 6000, 4000)])        # accumulates across calls
+        # ROI stacks to the host (full frames would be 31 GB): exactly the bytes LogoScan::AddFrame reads
+        Yr = fr[:, :ysz].view(n, h, w)[:, sy:sy + sh, sx:sx + sw].contiguous().cpu().numpy()
+        Ur = fr[:, ysz:ysz + csz].view(n, h // 2, w // 2)[:, sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2].contiguous().cpu().numpy()
+        Vr = fr[:, ysz + csz:].view(n, h // 2, w // 2)[:, sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2].contiguous().cpu().numpy()
+        o = po.RefScan(sw, sh, 12) if po.ref_available() else po.OracleScan(sw, sh, 12)
+        ov = np.array([o.add_frame(Yr[i], Ur[i], Vr[i]) for i in range(n)], np.uint8)
+        assert np.array_equal(valid, ov), (sw, sh, int((valid != ov).sum()))
+        assert 0 < int(ov.sum()) < n and acc.num_valid == o.nframes == int(ov.sum())
+        assert np.array_equal(acc.sums(), o.sums())              # exact integers (< 2^53) in doubles
+        for clean in (False, True):
+            a, b = acc.get_logo(255, clean), o.get_logo(255, clean)
+            assert a is not None and b is not None and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        del acc
+
+
+@pytest.mark.timeout(900)
+def test_whole_clip_1080p_against_reference_code(ctx, oracle):
+    """300 consecutive 1080p frames of the bench clip: every logo score bit-identical with the reference's own compiled
+    code, every combing counter identical with the spec (AVX2 form; scalar form on a subset)."""
+    po = oracle
+    w, h, n, imgx, imgy = 1920, 1080, 300, 1700, 60
+    lg = synth.make_logo(64, 64)
+    fr = _gen(0, n, w, h, logo=lg, imgx=imgx, imgy=imgy)
+    logo = ab.Logo.create(lg["data"], 64, 64, w, h, imgx, imgy).deint().create_mask(0.35)
+    prm = ab.default_comb_params()
+    s, c = ctx.scan_comb_frames(ab.yv12_clip(fr, w, h, n, True), [logo], prm)
+    s, c = s.cpu().numpy(), c.cpu().numpy()
+    host = fr.cpu().numpy()
+    b = po.CpuBench(w, h, lg["data"], imgx, imgy, po.usable_cpu_threads(), 0.35)
+    _, rs, rc = b.run(host, prm.as_list(), 3, "avx2")
+    _, _, rc_s = b.run(host[:24], prm.as_list(), 2, "scalar")
+    b.close()
+    assert np.array_equal(_bits(s[:, 0]), _bits(rs))
+    assert np.array_equal(c, rc) and np.array_equal(c[:24], rc_s)
+    # host-buffer path over the same clip (staged through HBM by the library): identical
+    s2, c2 = ctx.scan_comb_frames(ab.yv12_clip(host, w, h, n, False), [logo], prm)
+    assert np.array_equal(_bits(s2[:, 0]), _bits(rs)) and np.array_equal(c2, rc)
+
+
+def test_logo_outlives_its_context(native_lib):
+    """a logo only remembers the device ordinal, so closing the context that first evaluated it and
+    destroying / re-using the logo afterwards is legal."""
+    w, h = 256, 128
+    lg = synth.make_logo(64, 64)
+    fr = synth.make_frames(40, 4, w, h, device="cuda", logo=lg, imgx=160, imgy=32)
+    clip = ab.yv12_clip(fr, w, h, 4, True)
+    logo = ab.Logo.create(lg["data"], 64, 64, w, h, 160, 32).deint().create_mask(0.35)
+    c1 = ab.Context(0, torch.cuda.current_stream().cuda_stream)
+    a = c1.scan_frames(clip, [logo]).cpu().numpy()
+    c1.close()
+    c2 = ab.Context(0, torch.cuda.current_stream().cuda_stream)        # a second context may evaluate the same logo
+    b = c2.scan_frames(clip, [logo]).cpu().numpy()
+    c2.close()
+    assert np.array_equal(_bits(a), _bits(b))
+    del logo                                                            # destroyed after both contexts are gone
+    torch.cuda.synchronize()
