@@ -4,6 +4,7 @@
 #include "amtk_internal.h"
 #include "logo_kernels.cuh"
 #include "comb_kernels.cuh"
+#include "comb_stream.cuh"
 #include "scan_kernels.cuh"
 #include <algorithm>
 #include <cfloat>
@@ -265,6 +266,131 @@ static int pick_comb_R(int hY, int hC) {
   return best;
 }
 
+// ---- round-2 streaming kernel (comb_stream.cuh): independent warp streams, 8-bit samples ----------------------
+struct WsVariant { int R, stages, TH, boxH, smem; void (*kernel)(const WsArgs); };
+template <typename Cfg> static WsVariant make_ws() { return WsVariant{ Cfg::R, Cfg::STAGES, Cfg::TH, Cfg::BOXH, Cfg::SMEM, comb_ws_kernel<Cfg> }; }
+static const WsVariant* ws_variants(int* n) {
+  static const WsVariant v[] = { make_ws<WsCfg<17, 2>>(), make_ws<WsCfg<15, 2>>(), make_ws<WsCfg<16, 2>>(), make_ws<WsCfg<9, 2>>(), make_ws<WsCfg<15, 3>>() };
+  *n = (int)(sizeof(v) / sizeof(v[0]));
+  return v;
+}
+// rows per run for 4-run tiles: fewest wasted rows over luma + chroma, ties to the larger R (less halo per row)
+static int pick_ws_R(int hY, int hC) {
+  int best = 17; long long best_waste = -1;
+  for (int R : { 17, 16, 15 }) {
+    const int th = 4 * R;
+    const long long waste = 2LL * ((long long)((hY + th - 1) / th) * th - hY) + 2LL * ((long long)((hC + th - 1) / th) * th - hC);
+    if (best_waste < 0 || waste < best_waste) { best_waste = waste; best = R; }
+  }
+  return best;
+}
+
+static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi,
+                          const amtk_comb_params* prm, int* dcounts, int out_row0) {
+  const int hY = clip->height, hC = clip->height >> clip->log_uvy;
+  const int wY = clip->width, wC = clip->width >> clip->log_uvx;
+  const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_ws_R(hY, hC);
+  int nvar = 0; const WsVariant* vars = ws_variants(&nvar); const WsVariant* V = nullptr;
+  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].stages == ctx->knobs.comb_ws_stages) V = &vars[i];
+  if (!V) AMTK_FAIL("comb: no warp-stream kernel variant for the requested AMTK_COMB_* settings");
+  WsArgs args;
+  memset(&args, 0, sizeof(args));
+  const CUtensorMapL2promotion promo = ctx->knobs.comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : ctx->knobs.comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                       ctx->knobs.comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  for (int pl = 0; pl < 3; ++pl) {
+    const long long off = pl == 0 ? 0 : (pl == 1 ? clip->off_u : clip->off_v);
+    cuuint64_t gdim[3] = { (cuuint64_t)(pl ? wC : wY), (cuuint64_t)(pl ? hC : hY), (cuuint64_t)win.count };
+    cuuint64_t gstr[2] = { (cuuint64_t)(pl ? clip->pitch_uv : clip->pitch_y), (cuuint64_t)clip->frame_stride };
+    cuuint32_t box[3] = { (cuuint32_t)kWsTW, (cuuint32_t)V->boxH, 1u };
+    cuuint32_t estr[3] = { 1u, 1u, 1u };
+    if (ctx->encode_tiled(&args.map[pl], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      AMTK_FAIL("cuTensorMapEncodeTiled failed");
+  }
+  // chroma remainder columns of at most 64 bytes: U and V side by side in one tile through a 4-D map (x, plane, y, frame)
+  const int remC = wC % kWsTW;
+  const long long uv_dist = clip->off_v - clip->off_u;
+  const bool pair_uv = ctx->knobs.comb_merge_uv && remC > 0 && remC <= kWsTW / 2 && uv_dist > 0 && (uv_dist & 15) == 0;
+  if (pair_uv) {
+    cuuint64_t gdim[4] = { (cuuint64_t)wC, 2u, (cuuint64_t)hC, (cuuint64_t)win.count };
+    cuuint64_t gstr[3] = { (cuuint64_t)uv_dist, (cuuint64_t)clip->pitch_uv, (cuuint64_t)clip->frame_stride };
+    cuuint32_t box[4] = { (cuuint32_t)(kWsTW / 2), 2u, (cuuint32_t)V->boxH, 1u };
+    cuuint32_t estr[4] = { 1u, 1u, 1u, 1u };
+    if (ctx->encode_tiled(&args.map_uv, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(win.dev_base) + clip->off_u, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      AMTK_FAIL("cuTensorMapEncodeTiled(uv pair) failed");
+  }
+  const int tyY = (hY + V->TH - 1) / V->TH, tyC = (hC + V->TH - 1) / V->TH;
+  int tile0 = 0, nc = 0;
+  auto thresholds = [&](WsClass& C, bool chroma) {
+    C.cls = chroma ? 1 : 0; C.H = chroma ? hC : hY;
+    C.thM = (unsigned)(0x80 - (chroma ? prm->th_move_c : prm->th_move_y)) * 0x01010101u;
+    C.thS = (unsigned)(chroma ? prm->th_shima_c : prm->th_shima_y) * 0x00010001u;     // integer k in [1,2047] IS the fp16 bit pattern of k*2^-24
+    C.thL = (unsigned)(chroma ? prm->th_lshima_c : prm->th_lshima_y) * 0x00010001u;
+  };
+  for (int pl = 0; pl < 3; ++pl) {                         // 128-byte tiles of Y, U, V
+    WsClass& C = args.cl[nc];
+    const int w = pl ? wC : wY;
+    C.kind = 0; C.map = pl; thresholds(C, pl != 0);
+    C.tilesX = (pl && pair_uv) ? w / kWsTW : (w + kWsTW - 1) / kWsTW;
+    C.tile0 = tile0; C.ntiles = C.tilesX * (pl ? tyC : tyY);
+    if (C.ntiles == 0) continue;
+    tile0 += C.ntiles; ++nc;
+  }
+  if (pair_uv) {
+    WsClass& C = args.cl[nc];
+    C.kind = 1; C.x0 = wC - remC; C.tilesX = 1; thresholds(C, true);
+    C.tile0 = tile0; C.ntiles = tyC; tile0 += C.ntiles; ++nc;
+  }
+  args.nclasses = nc;
+  const int ntiles = tile0, nf = hi - lo;
+  int occ = 0;
+  AMTK_CUDA(cudaFuncSetAttribute(V->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
+  AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, V->kernel, 32 * kWsWarps, V->smem));
+  if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
+  if (ctx->knobs.comb_ctas > 0) occ = std::min(occ, ctx->knobs.comb_ctas);
+  // Work queue: every tile's frame range is cut into items; the warps pull items from a global counter.  Long items
+  // (little halo overhead: one extra tile load per item) make up the first ~85 % of the work, short ones the rest, so
+  // that all warps run dry within about one short item of each other.
+  const long long total = (long long)ntiles * nf;
+  const int nwarps = ctx->sm_count * occ * kWsWarps;
+  const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (total + kWsWarps - 1) / kWsWarps);
+  int big = ctx->knobs.comb_item > 0 ? ctx->knobs.comb_item : 64, small = std::max(4, big / 4);
+  // each warp should see at least ~6 big items; shrink for short clips
+  while (big > 8 && (long long)ntiles * (nf / big) < 6LL * nwarps) { big /= 2; small = std::max(4, big / 4); }
+  const int tail_frames = std::min(nf, std::max(small, (int)(nf * 0.15)));
+  const int head_frames = nf - tail_frames;
+  std::vector<CombSegment> segs;
+  segs.reserve((size_t)ntiles * (head_frames / big + tail_frames / small + 2));
+  const int f0 = lo - win.first;
+  for (int t = 0; t < ntiles; ++t)
+    for (int f = 0; f < head_frames; f += big) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(head_frames, f + big) });
+  for (int t = 0; t < ntiles; ++t)
+    for (int f = head_frames; f < nf; f += small) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(nf, f + small) });
+  const size_t seg_bytes = segs.size() * sizeof(CombSegment);
+  const size_t q_off = (seg_bytes + 255) & ~(size_t)255;
+  if (!ensure(&ctx->small, &ctx->small_bytes, q_off + 256)) return 0;
+  AMTK_CUDA(cudaMemcpyAsync(ctx->small, segs.data(), seg_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  AMTK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->small) + q_off, 0, 256, ctx->stream));
+  args.segs = reinterpret_cast<const CombSegment*>(ctx->small);
+  args.nitems = (int)segs.size();
+  args.queue = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ctx->small) + q_off);
+  args.counts = dcounts;
+  args.out_frame0 = out_row0 - win.first;
+  AMTK_CUDA(cudaMemsetAsync(dcounts + (size_t)(lo - out_row0) * 12, 0, (size_t)nf * 12 * sizeof(int), ctx->stream));
+  std::pair<cudaEvent_t, cudaEvent_t> ev{ nullptr, nullptr };
+  if (ctx->timing) {
+    if (!ctx->timing_pool.empty()) { ev = ctx->timing_pool.back(); ctx->timing_pool.pop_back(); }
+    else { AMTK_CUDA(cudaEventCreate(&ev.first)); AMTK_CUDA(cudaEventCreate(&ev.second)); }
+    AMTK_CUDA(cudaEventRecord(ev.first, ctx->stream));
+  }
+  V->kernel<<<grid, 32 * kWsWarps, V->smem, ctx->stream>>>(args);
+  AMTK_CUDA(cudaGetLastError());
+  if (ctx->timing) { AMTK_CUDA(cudaEventRecord(ev.second, ctx->stream)); ctx->timing_events.push_back(ev); }
+  ctx->launches += 1;
+  return 1;
+}
+
 static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi,
                        const amtk_comb_params* prm, int* dcounts, int out_row0) {
   const bool tma_layout = !((clip->frame_stride & 15) || (clip->pitch_y & 15) || (clip->pitch_uv & 15) || (clip->off_u & 15) ||
@@ -298,6 +424,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     }
     return 1;
   }
+  if (clip->bytes_per_sample == 1 && ctx->knobs.comb_ws) return launch_comb_ws(ctx, clip, win, lo, hi, prm, dcounts, out_row0);
   const int hY = clip->height, hC = clip->height >> clip->log_uvy;
   const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_comb_R(hY, hC);
   int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
@@ -477,6 +604,9 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_PART")) c->knobs.comb_part = atoi(e);
   if (const char* e = getenv("AMTK_EVAL_WAVES")) c->knobs.eval_waves = std::max(1, atoi(e));
   if (const char* e = getenv("AMTK_COMB_L2")) c->knobs.comb_l2 = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_WS")) c->knobs.comb_ws = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_WS_STAGES")) c->knobs.comb_ws_stages = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_ITEM")) c->knobs.comb_item = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }
   *out = c;

@@ -65,6 +65,9 @@ struct amtk_ctx {
     int comb_merge_uv = 1;  // U|V remainder columns share one tile
     int comb_part = -1;     // partition: -1 auto, 0 equal-share, 1 lock-step
     int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_sync = 0, comb_l2 = 64;
+    int comb_item = 0;        // frames per long work item of the warp-stream kernel (0 = auto)
+    int comb_ws_stages = 2;  // ring slots per warp stream
+    int comb_ws = 1;        // 1: round-2 warp-stream kernel for 8-bit clips (comb_stream.cuh); 0: round-1 CTA-ring kernel
   } knobs;
   // optional per-launch timing of the dominant (comb) kernel with CUDA events on the launching stream
   bool timing = false;
