@@ -270,7 +270,7 @@ static int pick_comb_R(int hY, int hC) {
 struct WsVariant { int R, stages, TH, boxH, smem; void (*kernel)(const WsArgs); };
 template <typename Cfg> static WsVariant make_ws() { return WsVariant{ Cfg::R, Cfg::STAGES, Cfg::TH, Cfg::BOXH, Cfg::SMEM, comb_ws_kernel<Cfg> }; }
 static const WsVariant* ws_variants(int* n) {
-  static const WsVariant v[] = { make_ws<WsCfg<17, 2>>(), make_ws<WsCfg<15, 2>>(), make_ws<WsCfg<16, 2>>(), make_ws<WsCfg<9, 2>>(), make_ws<WsCfg<15, 3>>() };
+  static const WsVariant v[] = { make_ws<WsCfg<17, 2>>(), make_ws<WsCfg<15, 2>>(), make_ws<WsCfg<16, 2>>(), make_ws<WsCfg<9, 2>>(), make_ws<WsCfg<15, 3>>(), make_ws<WsCfg<12, 2>>(), make_ws<WsCfg<10, 2>>() };
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }

@@ -41,7 +41,7 @@ struct WsCfg {
   static constexpr int STAGE_BYTES = kWsTW * BOXH;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;   // one warp's ring
   static constexpr int SMEM = kWsWarps * RING_BYTES + 128;  // + alignment slack
-  static constexpr int MIN_CTAS = (227 * 1024) / (SMEM + 1024) >= 3 ? 3 : 2;     // resident CTAs the register budget is set for
+  static constexpr int MIN_CTAS = (227 * 1024) / (SMEM + 1024 + 64) >= 4 ? 4 : (227 * 1024) / (SMEM + 1024 + 64) >= 3 ? 3 : 2;     // resident CTAs the register budget is set for
 };
 
 // A tile class: all tiles of one class have the same shape and are numbered consecutively from tile0.
@@ -83,6 +83,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 #define AMTK_WS_RELOAD_PREV 1
 #endif
 constexpr bool kWsReloadPrev = AMTK_WS_RELOAD_PREV != 0;
+#ifndef AMTK_WS_L_VIA_IDP
+#define AMTK_WS_L_VIA_IDP 0
+#endif
+constexpr bool kWsLviaIdp = AMTK_WS_L_VIA_IDP != 0;        // large-threshold counter: 510 per hit instead of pair-coded
 // an LDS.128 the compiler cannot merge with an earlier C++ load of the same address
 __device__ __forceinline__ uint4 lds128(const uint8_t* p) {
   uint4 v;
@@ -119,15 +123,26 @@ __device__ __forceinline__ void ws_row_masks(const H8& h0, const H8& h1, const H
     mS[q] = __hge2_mask(r, thS);
     mL[q] = __hge2_mask(r, thL);
   }
-  // 8 masks + accumulator = 9 operands = four 3-input adds
+  // 8 masks + accumulator = 9 operands = four 3-input adds (ALU pipe) ...
   accS = accS - (mS[0] + mS[1]) - (mS[2] + mS[3] + mS[4]) - (mS[5] + mS[6] + mS[7]);
-  accL = accL - (mL[0] + mL[1]) - (mL[2] + mL[3] + mL[4]) - (mL[5] + mL[6] + mL[7]);
+  if (kWsLviaIdp) {
+    // ... or, for the large-threshold masks, eight IDP.4A on the FMA-heavy pipe, which has the slack: the loop is
+    // ALU-pipe bound (HSET2/PRMT/LOP3/IADD3/VABSDIFF4 = 49 of 92 instructions per 16-pixel row).  A 0xFFFF lane is two
+    // 0xFF bytes, so the byte sum grows by 510 per hit.
+#pragma unroll
+    for (int q = 0; q < 8; ++q) accL = __dp4a(mL[q], 0x01010101u, accL);
+  } else {
+    accL = accL - (mL[0] + mL[1]) - (mL[2] + mL[3] + mL[4]) - (mL[5] + mL[6] + mL[7]);
+  }
 }
 
 // Main body: R rows of one lane's 16-byte strip.  cur points at smem row (run*R) of the box = global row y_first-2.
 // P[j] holds the previous frame's bytes of output row j (kept in REGISTERS from the step before: the centre row of step
 // k is exactly the "previous" row of step k+1, so the inter-frame difference costs neither a second shared-memory slot
 // nor a second LDS); on return P holds this frame's rows.
+// Per 16-pixel row: 32 HFMA2/HADD2 + 4 IDP + 4 IMAD.IADD on the FMA-heavy pipe; 16 HSET2 + 8 PRMT + 8 LOP3 + 8 IADD3 +
+// 4 VABSDIFF4 on the ALU pipe; 2 LDS.128.  (ptxas reschedules the unrolled body on its own: three different source
+// orders of this loop gave the identical SASS schedule.)
 template <int R, int PITCH>
 __device__ __forceinline__ WsCounts ws_rows(const uint8_t* __restrict__ cur, uint4 (&P)[R],
                                             const uint32_t kM, const uint32_t thS_bits, const uint32_t thL_bits) {
@@ -144,9 +159,9 @@ __device__ __forceinline__ WsCounts ws_rows(const uint8_t* __restrict__ cur, uin
   for (int j = 0; j < R; ++j) {
     const uint4 raw_nn = *reinterpret_cast<const uint4*>(cur + (j + 4) * PITCH);
     const uint4 pv = P[j];
-    const H8 h4 = bytes16_to_half(raw_nn);
     const int f = j & 1;
-    // inter-frame difference of the centre row (ALU pipe + IDP), ahead of the stencil (FMA pipe) of the same row
+    const H8 h4 = bytes16_to_half(raw_nn);
+    // inter-frame difference of the centre row: VABSDIFF4 + SWAR compare (ALU pipe), IDP.4A count (FMA pipe)
     c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.x, pv.x), kM), 0x01010101u, c.M[f]);
     c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.y, pv.y), kM), 0x01010101u, c.M[f]);
     c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.z, pv.z), kM), 0x01010101u, c.M[f]);
@@ -179,7 +194,7 @@ __device__ __noinline__ void ws_fixup(const uint8_t* cur, uint32_t rows, uint32_
     const H8 h3 = bytes16_to_half(*reinterpret_cast<const uint4*>(p + 3 * PITCH));
     const H8 h4 = bytes16_to_half(*reinterpret_cast<const uint4*>(p + 4 * PITCH));
     uint32_t dS = 0u, dL = 0u;
-    ws_row_masks(h0, h1, h2, h3, h4, thS, thL, dS, dL);      // dS = -(masks)
+    ws_row_masks(h0, h1, h2, h3, h4, thS, thL, dS, dL);      // what the body added for this row (mod 2^32)
     c.S[j & 1] -= dS; c.L[j & 1] -= dL;
   }
 }
@@ -275,8 +290,8 @@ __global__ void __launch_bounds__(32 * kWsWarps, Cfg::MIN_CTAS) comb_ws_kernel(c
       if (lane < 6) {                                        // lane = field*3 + metric = the counts[] layout of one class
         const int fld = lane >= 3, met = lane - 3 * fld;
         uint32_t v = met == 0 ? (fld ? rM1 : rM0) : met == 1 ? (fld ? rS1 : rS0) : (fld ? rL1 : rL0);
-        v = met == 0 ? (v >> 7) : decode_pair(v);
-        if (v) atomicAdd(crow + (size_t)k * 12, (int)v);
+        v = met == 0 ? (v >> 7) : (met == 2 && kWsLviaIdp) ? v / 510u : decode_pair(v);
+        if (v) atomicAdd(crow + (size_t)k * 12, (int)v);     // (an unconditional RED measured 3 % slower: hot counter lines)
       }
     }
     gload += (uint32_t)nloads;
