@@ -52,6 +52,7 @@ SIGNATURES = [
     ("amtk_ctx_destroy", None, [V]),
     ("amtk_ctx_synchronize", C.c_int, [V]),
     ("amtk_ctx_launch_count", C.c_int64, [V]),
+    ("amtk_ctx_last_h2d_bytes", C.c_int64, [V]),
     ("amtk_ctx_set_kernel_timing", C.c_int, [V, C.c_int]),
     ("amtk_ctx_get_kernel_timing", C.c_int, [V, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     ("amtk_probe_read_ms", C.c_int, [V, V, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
@@ -173,6 +174,10 @@ class Context:
     @property
     def launches(self):
         return int(self.L.amtk_ctx_launch_count(self.h))
+
+    @property
+    def last_h2d_bytes(self):
+        return int(self.L.amtk_ctx_last_h2d_bytes(self.h))
 
     def set_kernel_timing(self, enable):
         check(self.L.amtk_ctx_set_kernel_timing(self.h, int(enable)))

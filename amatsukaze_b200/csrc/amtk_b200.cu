@@ -44,7 +44,8 @@ static bool ensure(void** p, size_t* cap, size_t need) {
 
 struct DevSelect {   // RAII: make a device (the context's, or an ordinal) current for the duration of a call
   int prev = -1; bool ok = true;
-  explicit DevSelect(const amtk_ctx* c) : DevSelect(c->device) {}
+  std::unique_lock<std::recursive_mutex> lock;     // held for the whole entry point when constructed from a context
+  explicit DevSelect(const amtk_ctx* c) : DevSelect(c->device) { lock = std::unique_lock<std::recursive_mutex>(c->mu); }
   explicit DevSelect(int device) { ok = cuda_ok(cudaGetDevice(&prev), "cudaGetDevice") && cuda_ok(cudaSetDevice(device), "cudaSetDevice"); }
   ~DevSelect() { if (prev >= 0) cudaSetDevice(prev); }
 };
@@ -86,6 +87,7 @@ static int for_each_window(amtk_ctx* ctx, const amtk_clip* clip, int frame0, int
     ctx->stage_bytes = need;
   }
   int chunk = 0;
+  long long h2d = 0;
   for (int lo = frame0; lo < frame0 + nframes; lo += per, ++chunk) {
     const int hi = std::min(frame0 + nframes, lo + per);
     const int b = chunk & 1;
@@ -98,7 +100,100 @@ static int for_each_window(amtk_ctx* ctx, const amtk_clip* clip, int frame0, int
     Window w{ reinterpret_cast<const uint8_t*>(ctx->stage[b]), first, hi - first };
     if (!fn(w, lo, hi)) return 0;
     AMTK_CUDA(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    h2d += (long long)(hi - first) * (long long)fs;
   }
+  ctx->h2d_bytes_last = h2d;
+  return 1;
+}
+
+// ROI-only staging of HOST clips for the entry points that read nothing but a rectangle of every frame
+// (LogoFrame::ScanFrame, AMTAnalyzeLogo, ReMakeLogo's fade sweep, LogoScan::AddFrame, AMTEraseLogo -- the reference
+// itself touches only the ROI there, LogoScan.hpp:1559-1566,1146-1155,606-635,1374-1397).  Instead of moving whole frames
+// over PCIe (3.1 MB each for a 6 KB rectangle) the library copies the rectangle rows of Y (and U, V) into a compact
+// clip in HBM with strided 3-D copies and runs the same kernels on that clip with shifted coordinates.
+// fn(vclip, window, lo, hi, dx, dy): vclip describes the resident data; luma sample (x, y) of the real frame is at
+// (x - dx, y - dy) in vclip (chroma: shifted by dx >> log_uvx, dy >> log_uvy).  write_back copies the rectangles back
+// to the host frames after fn (in-place erase).
+template <typename Fn>
+static int for_each_roi_window(amtk_ctx* ctx, const amtk_clip* clip, int frame0, int nframes, int rx, int ry, int rw, int rh,
+                               bool with_chroma, bool write_back, Fn fn) {
+  if (frame0 < 0 || nframes < 0 || frame0 + nframes > clip->num_frames) AMTK_FAIL("frame range outside the clip");
+  if (nframes == 0) return 1;
+  if (clip->on_device) {
+    Window w{ reinterpret_cast<const uint8_t*>(clip->base), 0, clip->num_frames };
+    return fn(*clip, w, frame0, frame0 + nframes, 0, 0);
+  }
+  const int bps = clip->bytes_per_sample, lx = clip->log_uvx, ly = clip->log_uvy;
+  const int A = 16 << lx;                                              // luma byte alignment that keeps chroma 16-byte aligned
+  const int xb0 = ((rx * bps) / A) * A;
+  const int xb1 = std::min(clip->pitch_y, (((rx + rw) * bps + A - 1) / A) * A);
+  const int cp = ((xb1 - xb0 + A - 1) / A) * A;                        // compact luma pitch (bytes); chroma pitch = cp >> lx
+  const int dy = ry & ~((1 << ly) - 1);
+  const int y1 = std::min(clip->height, (ry + rh + (1 << ly) - 1) & ~((1 << ly) - 1));
+  const int rowsY = y1 - dy, rowsC = with_chroma ? (rowsY >> ly) : 0;
+  const int cpc = cp >> lx, spanY = xb1 - xb0;
+  const int xc0 = xb0 >> lx, spanC = std::min(clip->pitch_uv - xc0, spanY >> lx);
+  // plane offsets are whole rows of the luma pitch, so the frame stride is a multiple of both pitches (3-D copies)
+  const int rows_u = rowsY, rows_c_as_y = (int)(((long long)cpc * rowsC + cp - 1) / cp);
+  const long long offU = (long long)cp * rows_u, offV = offU + (long long)cp * rows_c_as_y;
+  const long long fs = with_chroma ? offV + (long long)cp * rows_c_as_y : (long long)cp * rowsY;
+  if (cp <= 0 || rowsY <= 0 || (with_chroma && spanC <= 0)) AMTK_FAIL("ROI staging: empty rectangle");
+  size_t budget = (size_t)256 << 20;
+  if (const char* e = getenv("AMTK_STAGE_MB")) budget = (size_t)std::max(1, atoi(e)) << 20;
+  const int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)nframes, budget / (size_t)fs));
+  const size_t need = (size_t)per * (size_t)fs;
+  if (ctx->stage_bytes < need) {
+    for (int b = 0; b < 2; ++b) { if (ctx->stage[b]) cudaFree(ctx->stage[b]); ctx->stage[b] = nullptr; }
+    ctx->stage_bytes = 0;
+    for (int b = 0; b < 2; ++b) AMTK_CUDA(cudaMalloc(&ctx->stage[b], std::max(need, (size_t)1 << 20)));
+    ctx->stage_bytes = std::max(need, (size_t)1 << 20);
+  }
+  amtk_clip v = *clip;
+  v.frame_stride = fs; v.off_u = offU; v.off_v = offV;
+  v.width = cp / bps; v.height = rowsY; v.pitch_y = cp; v.pitch_uv = cpc; v.on_device = 1;
+  const uint8_t* hbase = reinterpret_cast<const uint8_t*>(clip->base);
+  // one strided copy per plane and chunk (cudaMemcpy3D: x = bytes of a rectangle row, y = rows, z = frames); falls back
+  // to one 2-D copy per frame when the frame stride is not a whole number of rows
+  auto copy_plane = [&](int pl, uint8_t* dev, int first, int count, bool to_host, cudaStream_t st) -> bool {
+    const long long hoff = pl == 0 ? 0 : (pl == 1 ? clip->off_u : clip->off_v);
+    const int hp = pl ? clip->pitch_uv : clip->pitch_y, dp = pl ? cpc : cp;
+    const int span = pl ? spanC : spanY, rows = pl ? rowsC : rowsY;
+    const long long doff = pl == 0 ? 0 : (pl == 1 ? offU : offV);
+    uint8_t* h = const_cast<uint8_t*>(hbase) + (long long)first * clip->frame_stride + hoff + (long long)(pl ? (dy >> ly) : dy) * hp + (pl ? xc0 : xb0);
+    uint8_t* d = dev + doff;
+    if (clip->frame_stride % hp == 0 && fs % dp == 0) {
+      cudaMemcpy3DParms p3; memset(&p3, 0, sizeof(p3));
+      const cudaPitchedPtr hptr = make_cudaPitchedPtr(h, (size_t)hp, (size_t)hp, (size_t)(clip->frame_stride / hp));
+      const cudaPitchedPtr dptr = make_cudaPitchedPtr(d, (size_t)dp, (size_t)dp, (size_t)(fs / dp));
+      p3.srcPtr = to_host ? dptr : hptr; p3.dstPtr = to_host ? hptr : dptr;
+      p3.extent = make_cudaExtent((size_t)span, (size_t)rows, (size_t)count);
+      p3.kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+      return cuda_ok(cudaMemcpy3DAsync(&p3, st), "cudaMemcpy3DAsync(roi)");
+    }
+    for (int f = 0; f < count; ++f) {
+      uint8_t* hf = h + (long long)f * clip->frame_stride; uint8_t* df = d + (long long)f * fs;
+      if (!cuda_ok(to_host ? cudaMemcpy2DAsync(hf, hp, df, dp, span, rows, cudaMemcpyDeviceToHost, st)
+                           : cudaMemcpy2DAsync(df, dp, hf, hp, span, rows, cudaMemcpyHostToDevice, st), "cudaMemcpy2DAsync(roi)")) return false;
+    }
+    return true;
+  };
+  int chunk = 0;
+  for (int lo = frame0; lo < frame0 + nframes; lo += per, ++chunk) {
+    const int hi = std::min(frame0 + nframes, lo + per);
+    const int b = chunk & 1;
+    uint8_t* dev = reinterpret_cast<uint8_t*>(ctx->stage[b]);
+    AMTK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));      // previous user of this buffer
+    for (int pl = 0; pl < (with_chroma ? 3 : 1); ++pl) if (!copy_plane(pl, dev, lo, hi - lo, false, ctx->copy_stream)) return 0;
+    AMTK_CUDA(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+    AMTK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+    v.base = dev; v.num_frames = hi - lo;
+    Window w{ dev, lo, hi - lo };
+    if (!fn(v, w, lo, hi, xb0 / bps, dy)) return 0;
+    if (write_back)
+      for (int pl = 0; pl < (with_chroma ? 3 : 1); ++pl) if (!copy_plane(pl, dev, lo, hi - lo, true, ctx->stream)) return 0;
+    AMTK_CUDA(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+  }
+  ctx->h2d_bytes_last = (long long)nframes * ((long long)spanY * rowsY + (with_chroma ? 2LL * spanC * rowsC : 0));
   return 1;
 }
 
@@ -344,37 +439,51 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   }
   args.nclasses = nc;
   const int ntiles = tile0, nf = hi - lo;
-  int occ = 0;
-  AMTK_CUDA(cudaFuncSetAttribute(V->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
-  AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, V->kernel, 32 * kWsWarps, V->smem));
-  if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
+  amtk_ctx::CombPlan& plan = ctx->plan;
+  if (plan.occ_kernel != (const void*)V->kernel) {          // once per kernel variant, not per launch
+    int occ = 0;
+    AMTK_CUDA(cudaFuncSetAttribute(V->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
+    AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, V->kernel, 32 * kWsWarps, V->smem));
+    if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
+    plan.occ = occ; plan.occ_kernel = (const void*)V->kernel; plan.valid = false;
+  }
+  int occ = plan.occ;
   if (ctx->knobs.comb_ctas > 0) occ = std::min(occ, ctx->knobs.comb_ctas);
   // Work queue: every tile's frame range is cut into items; the warps pull items from a global counter.  Long items
   // (little halo overhead: one extra tile load per item) make up the first ~85 % of the work, short ones the rest, so
-  // that all warps run dry within about one short item of each other.
+  // that all warps run dry within about one short item of each other.  The item list depends only on the geometry and
+  // the frame range, so it stays on the device between calls (a 1-frame GetFrame call re-uses it without any copy).
   const long long total = (long long)ntiles * nf;
   const int nwarps = ctx->sm_count * occ * kWsWarps;
   const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (total + kWsWarps - 1) / kWsWarps);
-  int big = ctx->knobs.comb_item > 0 ? ctx->knobs.comb_item : 64, small = std::max(4, big / 4);
-  // each warp should see at least ~6 big items; shrink for short clips
-  while (big > 8 && (long long)ntiles * (nf / big) < 6LL * nwarps) { big /= 2; small = std::max(4, big / 4); }
-  const int tail_frames = std::min(nf, std::max(small, (int)(nf * 0.15)));
-  const int head_frames = nf - tail_frames;
-  std::vector<CombSegment> segs;
-  segs.reserve((size_t)ntiles * (head_frames / big + tail_frames / small + 2));
   const int f0 = lo - win.first;
-  for (int t = 0; t < ntiles; ++t)
-    for (int f = 0; f < head_frames; f += big) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(head_frames, f + big) });
-  for (int t = 0; t < ntiles; ++t)
-    for (int f = head_frames; f < nf; f += small) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(nf, f + small) });
-  const size_t seg_bytes = segs.size() * sizeof(CombSegment);
-  const size_t q_off = (seg_bytes + 255) & ~(size_t)255;
-  if (!ensure(&ctx->small, &ctx->small_bytes, q_off + 256)) return 0;
-  AMTK_CUDA(cudaMemcpyAsync(ctx->small, segs.data(), seg_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  AMTK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->small) + q_off, 0, 256, ctx->stream));
-  args.segs = reinterpret_cast<const CombSegment*>(ctx->small);
-  args.nitems = (int)segs.size();
-  args.queue = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ctx->small) + q_off);
+  if (!(plan.valid && plan.wY == wY && plan.hY == hY && plan.wC == wC && plan.hC == hC && plan.nf == nf && plan.f0 == f0 &&
+        plan.R == V->R && plan.item == ctx->knobs.comb_item && plan.ctas == occ)) {
+    int big = ctx->knobs.comb_item > 0 ? ctx->knobs.comb_item : 64, small = std::max(4, big / 4);
+    // each warp should see at least ~6 big items; shrink for short clips
+    while (big > 8 && (long long)ntiles * (nf / big) < 6LL * nwarps) { big /= 2; small = std::max(4, big / 4); }
+    const int tail_frames = std::min(nf, std::max(small, (int)(nf * 0.15)));
+    const int head_frames = nf - tail_frames;
+    std::vector<CombSegment> segs;
+    segs.reserve((size_t)ntiles * (head_frames / big + tail_frames / small + 2));
+    for (int t = 0; t < ntiles; ++t)
+      for (int f = 0; f < head_frames; f += big) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(head_frames, f + big) });
+    for (int t = 0; t < ntiles; ++t)
+      for (int f = head_frames; f < nf; f += small) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(nf, f + small) });
+    const size_t seg_bytes = segs.size() * sizeof(CombSegment);
+    plan.q_off = (seg_bytes + 255) & ~(size_t)255;
+    plan.valid = false;
+    if (!ensure(&plan.dev, &plan.cap, plan.q_off + 256)) return 0;
+    AMTK_CUDA(cudaMemcpyAsync(plan.dev, segs.data(), seg_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    AMTK_CUDA(cudaStreamSynchronize(ctx->stream));           // pageable source vector dies at the end of this scope
+    plan.nitems = (int)segs.size();
+    plan.wY = wY; plan.hY = hY; plan.wC = wC; plan.hC = hC; plan.nf = nf; plan.f0 = f0; plan.R = V->R;
+    plan.item = ctx->knobs.comb_item; plan.ctas = occ; plan.valid = true;
+  }
+  AMTK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(plan.dev) + plan.q_off, 0, 256, ctx->stream));
+  args.segs = reinterpret_cast<const CombSegment*>(plan.dev);
+  args.nitems = plan.nitems;
+  args.queue = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(plan.dev) + plan.q_off);
   args.counts = dcounts;
   args.out_frame0 = out_row0 - win.first;
   AMTK_CUDA(cudaMemsetAsync(dcounts + (size_t)(lo - out_row0) * 12, 0, (size_t)nf * 12 * sizeof(int), ctx->stream));
@@ -623,6 +732,7 @@ void amtk_ctx_destroy(amtk_ctx* c) {
   if (c->small) cudaFree(c->small);
   if (c->dout) cudaFree(c->dout);
   if (c->dout2) cudaFree(c->dout2);
+  if (c->plan.dev) cudaFree(c->plan.dev);
   for (auto* v : { &c->timing_events, &c->timing_pool }) for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   cudaSetDevice(prev);
@@ -636,6 +746,7 @@ int amtk_ctx_synchronize(amtk_ctx* c) {
   return 1;
 }
 int64_t amtk_ctx_launch_count(const amtk_ctx* c) { return c ? c->launches : 0; }
+int64_t amtk_ctx_last_h2d_bytes(const amtk_ctx* c) { return c ? c->h2d_bytes_last : 0; }
 
 int amtk_ctx_set_kernel_timing(amtk_ctx* c, int enable) {
   if (!c) AMTK_FAIL("null context");
@@ -863,23 +974,40 @@ static int finish_output(amtk_ctx* ctx, void* host_dst, const void* dev_src, siz
   return 1;
 }
 
-static int scan_frames_impl(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
+// `real` is the caller's clip (frame size checks), `clip` the resident data (the same, or an ROI-only staging copy whose
+// luma origin sits at (dx, dy) of the real frame).
+static int scan_frames_impl(amtk_ctx* ctx, const amtk_clip* real, const amtk_clip* clip, int dx, int dy, amtk_logo* const* logos, int nlogos,
                             const Window& win, int lo, int hi, int pitch_override, float* dscores, int row0) {
   static const float kFades01[2] = { 0.0f, 1.0f };
   const int pitch = pitch_override > 0 ? pitch_override : clip->pitch_y / clip->bytes_per_sample;
+  const int real_pitch = pitch_override > 0 ? pitch_override : real->pitch_y / real->bytes_per_sample;
   for (int i = 0; i < nlogos; ++i) {
     const amtk_logo* lg = logos[i];
     float* o = dscores + (size_t)(lo - row0) * nlogos * 2;
-    if (!lg || lg->host.imgw != clip->width || lg->host.imgh != clip->height) {      // LogoScan.hpp:1551-1558
+    if (!lg || lg->host.imgw != real->width || lg->host.imgh != real->height) {      // LogoScan.hpp:1551-1558
       fill_pairs_kernel<<<(hi - lo + 127) / 128, 128, 0, ctx->stream>>>(o, hi - lo, nlogos * 2, i * 2, 0.0f, -1.0f);
       AMTK_CUDA(cudaGetLastError()); ctx->launches += 1;
       continue;
     }
-    if (!roi_inside(lg->host, clip, pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
-    EvalSpec sp{ lg, lg->host.imgx, lg->host.imgy, lg->host.w, lg->host.h, 0, 0, lg->host.w, 2, kFades01, 0, i * 2, 1 };
+    if (!roi_inside(lg->host, real, real_pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
+    EvalSpec sp{ lg, lg->host.imgx - dx, lg->host.imgy - dy, lg->host.w, lg->host.h, 0, 0, lg->host.w, 2, kFades01, 0, i * 2, 1 };
     if (!launch_eval(ctx, clip, win, lo, hi, pitch, sp, dscores, nlogos * 2, row0)) return 0;
   }
   return 1;
+}
+
+// bounding box of the rectangles of all logos that will be evaluated on `clip` (false when there is none)
+static bool logos_bbox(const amtk_clip* clip, amtk_logo* const* logos, int nlogos, int* rx, int* ry, int* rw, int* rh) {
+  int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+  for (int i = 0; i < nlogos; ++i) {
+    const amtk_logo* lg = logos[i];
+    if (!lg || lg->host.imgw != clip->width || lg->host.imgh != clip->height) continue;
+    x0 = std::min(x0, lg->host.imgx); y0 = std::min(y0, lg->host.imgy);
+    x1 = std::max(x1, lg->host.imgx + lg->host.w); y1 = std::max(y1, lg->host.imgy + lg->host.h);
+  }
+  if (x1 < 0 || x0 < 0 || y0 < 0 || x1 > clip->width || y1 > clip->height) return false;
+  *rx = x0; *ry = y0; *rw = x1 - x0; *rh = y1 - y0;
+  return true;
 }
 
 int amtk_logo_scan_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const* logos, int nlogos,
@@ -891,20 +1019,26 @@ int amtk_logo_scan_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const
   const size_t bytes = (size_t)nframes * nlogos * 2 * sizeof(float);
   float* d = out;
   if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
-  if (!for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
-        return scan_frames_impl(ctx, clip, logos, nlogos, w, lo, hi, pitch_override, d, frame0); }))
+  int rx, ry, rw, rh;
+  if (!clip->on_device && pitch_override <= 0 && logos_bbox(clip, logos, nlogos, &rx, &ry, &rw, &rh)) {
+    // host frames: only the logo rectangles cross PCIe (the reference reads nothing else, LogoScan.hpp:1559-1566)
+    if (!for_each_roi_window(ctx, clip, frame0, nframes, rx, ry, rw, rh, false, false,
+                             [&](const amtk_clip& v, const Window& w, int lo, int hi, int dx, int dy) {
+          return scan_frames_impl(ctx, clip, &v, dx, dy, logos, nlogos, w, lo, hi, 0, d, frame0); }))
+      return 0;
+  } else if (!for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
+        return scan_frames_impl(ctx, clip, clip, 0, 0, logos, nlogos, w, lo, hi, pitch_override, d, frame0); }))
     return 0;
   return finish_output(ctx, out, d, bytes, out_on_device);
 }
 
-static int analyze_impl(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* dl, const amtk_logo* ft, const amtk_logo* fb,
+static int analyze_impl(amtk_ctx* ctx, const amtk_clip* clip, int dx, int dy, const amtk_logo* dl, const amtk_logo* ft, const amtk_logo* fb,
                         const Window& win, int lo, int hi, float* dout, int row0) {
   float fades[11];
   for (int f = 0; f <= 10; ++f) fades[f] = (float)f / 10.0f;             // LogoScan.hpp:1152
   const int pitch = clip->pitch_y / clip->bytes_per_sample;
   const int w = dl->host.w, h = dl->host.h;
-  if (!roi_inside(dl->host, clip, pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
-  const int rx = dl->host.imgx, ry = dl->host.imgy;
+  const int rx = dl->host.imgx - dx, ry = dl->host.imgy - dy;
   EvalSpec sp{ dl, rx, ry, w, h, 0, 0, w, 11, fades, 1, 0, 1 };                // p[f]: deint logo on DeintY
   EvalSpec st{ ft, rx, ry, w, h, 1, 0, 2 * w, 11, fades, 1, 11, 1 };           // t[f]: top field logo on CopyY, stride 2w
   EvalSpec sb{ fb, rx, ry, w, h, 1, w, 2 * w, 11, fades, 1, 22, 1 };           // b[f]: bottom field logo on CopyY + w
@@ -924,8 +1058,10 @@ int amtk_logo_analyze_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_lo
   const size_t bytes = (size_t)nframes * 33 * sizeof(float);
   float* d = out;
   if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
-  if (!for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
-        return analyze_impl(ctx, clip, dl, ft, fb, w, lo, hi, d, frame0); }))
+  if (!roi_inside(dl->host, clip, clip->pitch_y / clip->bytes_per_sample)) AMTK_FAIL("logo rectangle lies outside the frame");
+  if (!for_each_roi_window(ctx, clip, frame0, nframes, dl->host.imgx, dl->host.imgy, dl->host.w, dl->host.h, false, false,
+                           [&](const amtk_clip& v, const Window& w, int lo, int hi, int dx, int dy) {
+        return analyze_impl(ctx, &v, dx, dy, dl, ft, fb, w, lo, hi, d, frame0); }))
     return 0;
   return finish_output(ctx, out, d, bytes, out_on_device);
 }
@@ -942,9 +1078,10 @@ int amtk_logo_eval_fades(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* 
   if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
   const int pitch = clip->pitch_y / clip->bytes_per_sample;
   if (!roi_inside(dl->host, clip, pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
-  EvalSpec sp{ dl, dl->host.imgx, dl->host.imgy, dl->host.w, dl->host.h, 0, 0, dl->host.w, nfades, fades, 0, 0, 1 };
-  if (!for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
-        return launch_eval(ctx, clip, w, lo, hi, pitch, sp, d, nfades, frame0); }))
+  if (!for_each_roi_window(ctx, clip, frame0, nframes, dl->host.imgx, dl->host.imgy, dl->host.w, dl->host.h, false, false,
+                           [&](const amtk_clip& v, const Window& w, int lo, int hi, int dx, int dy) {
+        EvalSpec sp{ dl, dl->host.imgx - dx, dl->host.imgy - dy, dl->host.w, dl->host.h, 0, 0, dl->host.w, nfades, fades, 0, 0, 1 };
+        return launch_eval(ctx, &v, w, lo, hi, v.pitch_y / v.bytes_per_sample, sp, d, nfades, frame0); }))
     return 0;
   return finish_output(ctx, out, d, bytes, out_on_device);
 }
@@ -987,7 +1124,7 @@ int amtk_scan_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const
   }
   if (!for_each_window(ctx, clip, frame0, nframes, true, [&](const Window& w, int lo, int hi) {
         return launch_comb(ctx, clip, w, lo, hi, prm, dc, frame0) &&
-               scan_frames_impl(ctx, clip, logos, nlogos, w, lo, hi, 0, ds_, frame0); }))
+               scan_frames_impl(ctx, clip, clip, 0, 0, logos, nlogos, w, lo, hi, 0, ds_, frame0); }))
     return 0;
   if (out_on_device) return 1;
   AMTK_CUDA(cudaMemcpyAsync(scores, ds_, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1036,11 +1173,13 @@ int amtk_scan_add_frames(amtk_scan* s, const amtk_clip* clip, int scanx, int sca
   uint8_t* base = reinterpret_cast<uint8_t*>(ctx->dout);
   int4* dbg = reinterpret_cast<int4*>(base); uint8_t* dsel = base + off_sel; uint8_t* dval = base + off_val;
   if (frame_select) AMTK_CUDA(cudaMemcpyAsync(dsel, frame_select, (size_t)nframes, cudaMemcpyHostToDevice, ctx->stream));
-  const int ok = for_each_window(ctx, clip, frame0, nframes, false, [&](const Window& w, int lo, int hi) {
+  // host clips: only the scan rectangle (Y, U, V) is uploaded -- LogoScan::AddFrame reads nothing else (LogoScan.hpp:606-635)
+  const int ok = for_each_roi_window(ctx, clip, frame0, nframes, scanx, scany, s->scanw, s->scanh, true, false,
+                                     [&](const amtk_clip& v, const Window& w, int lo, int hi, int dx, int dy) {
     ScanClip c;
-    c.base = w.dev_base; c.frame_stride = clip->frame_stride; c.offU = clip->off_u; c.offV = clip->off_v;
-    c.pitchY = clip->pitch_y; c.pitchUV = clip->pitch_uv;
-    c.scanx = scanx; c.scany = scany; c.scanw = s->scanw; c.scanh = s->scanh; c.logUVx = s->logUVx; c.logUVy = s->logUVy; c.thy = s->thy;
+    c.base = w.dev_base; c.frame_stride = v.frame_stride; c.offU = v.off_u; c.offV = v.off_v;
+    c.pitchY = v.pitch_y; c.pitchUV = v.pitch_uv;
+    c.scanx = scanx - dx; c.scany = scany - dy; c.scanw = s->scanw; c.scanh = s->scanh; c.logUVx = s->logUVx; c.logUVy = s->logUVy; c.thy = s->thy;
     c.frame0 = lo - w.first; c.nframes = hi - lo;
     const int rel = lo - frame0;
     scan_border_kernel<<<hi - lo, 256, 0, ctx->stream>>>(c, frame_select ? dsel + rel : nullptr, dbg + rel);
@@ -1159,7 +1298,6 @@ int amtk_scan_logo(amtk_ctx* ctx, const amtk_clip* clip, int service_id, const c
 int amtk_erase_logo_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* logo, int frame0, int nframes, const float* fades) {
   if (!ctx || !logo || !fades) AMTK_FAIL("amtk_erase_logo_frames: bad argument");
   if (!validate_clip(clip, true)) return 0;
-  if (!clip->on_device) AMTK_FAIL("amtk_erase_logo_frames: clip must be device resident (frames are edited in place in HBM)");
   const amtk::HostLogo& h = logo->host;
   if (h.imgx < 0 || h.imgy < 0 || h.imgx + h.w > clip->width || h.imgy + h.h > clip->height) AMTK_FAIL("logo rectangle lies outside the frame");
   if (frame0 < 0 || nframes < 0 || frame0 + nframes > clip->num_frames) AMTK_FAIL("frame range outside the clip");
@@ -1168,20 +1306,28 @@ int amtk_erase_logo_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo
   if (!logo_ensure_device(logo, ctx, false)) return 0;
   if (!ensure(&ctx->dout, &ctx->dout_bytes, (size_t)nframes * 2 * sizeof(float))) return 0;
   AMTK_CUDA(cudaMemcpyAsync(ctx->dout, fades, (size_t)nframes * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  EraseJob j;
-  j.base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(clip->base)); j.frame_stride = clip->frame_stride;
-  j.offU = clip->off_u; j.offV = clip->off_v;
-  j.pitchY = clip->pitch_y / clip->bytes_per_sample; j.pitchUV = clip->pitch_uv / clip->bytes_per_sample;
-  j.frame0 = frame0; j.nframes = nframes;
-  j.w = h.w; j.h = h.h; j.logUVx = h.logUVx; j.logUVy = h.logUVy; j.imgx = h.imgx; j.imgy = h.imgy;
-  j.aY = logo->dA; j.bY = logo->dB; j.aU = logo->dAU; j.bU = logo->dBU; j.aV = logo->dAV; j.bV = logo->dBV;
-  j.fades = reinterpret_cast<const float*>(ctx->dout);
-  j.maxv = (float)((1 << clip->bits_per_sample) - 1);
-  if (clip->bytes_per_sample == 1) erase_logo_kernel<uint8_t><<<nframes, 256, 0, ctx->stream>>>(j);
-  else erase_logo_kernel<uint16_t><<<nframes, 256, 0, ctx->stream>>>(j);
-  AMTK_CUDA(cudaGetLastError());
-  ctx->launches += 1;
-  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));    // `fades` staging buffer is reused by later calls
+  // Device clips are edited in place in HBM.  Host clips (the IClip::GetFrame surface: one MakeWritable'd CPU frame) move
+  // only the three logo rectangles: up, Delogo kernel, back down -- not the reference's full-frame copy (LogoScan.hpp:1347).
+  const int ok = for_each_roi_window(ctx, clip, frame0, nframes, h.imgx, h.imgy, h.w, h.h, true, true,
+                                     [&](const amtk_clip& v, const Window& w, int lo, int hi, int dx, int dy) {
+    EraseJob j;
+    j.base = const_cast<uint8_t*>(w.dev_base); j.frame_stride = v.frame_stride;
+    j.offU = v.off_u; j.offV = v.off_v;
+    j.pitchY = v.pitch_y / v.bytes_per_sample; j.pitchUV = v.pitch_uv / v.bytes_per_sample;
+    j.frame0 = lo - w.first; j.nframes = hi - lo;
+    j.w = h.w; j.h = h.h; j.logUVx = h.logUVx; j.logUVy = h.logUVy; j.imgx = h.imgx - dx; j.imgy = h.imgy - dy;
+    j.uvparity = (h.imgy / 2) % 2;                                             // LogoScan.hpp:1385, real frame position
+    j.aY = logo->dA; j.bY = logo->dB; j.aU = logo->dAU; j.bU = logo->dBU; j.aV = logo->dAV; j.bV = logo->dBV;
+    j.fades = reinterpret_cast<const float*>(ctx->dout) + (size_t)(lo - frame0) * 2;
+    j.maxv = (float)((1 << v.bits_per_sample) - 1);
+    if (v.bytes_per_sample == 1) erase_logo_kernel<uint8_t><<<hi - lo, 256, 0, ctx->stream>>>(j);
+    else erase_logo_kernel<uint16_t><<<hi - lo, 256, 0, ctx->stream>>>(j);
+    AMTK_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+  });
+  if (!ok) return 0;
+  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));    // `fades` staging buffer is reused by later calls; host frames are complete
   return 1;
 }
 

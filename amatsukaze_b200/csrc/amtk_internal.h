@@ -44,6 +44,11 @@ struct LogoDev {
 }  // namespace amtk
 
 struct amtk_ctx {
+  // One context = one device + one stream + one set of scratch buffers.  Entry points serialise on this mutex (taken by
+  // DevSelect), so concurrent calls on ONE context from several host threads (AviSynth Prefetch threads calling GetFrame
+  // on MT_NICE_FILTER filters) are safe; calls on distinct contexts run concurrently.  Recursive: amtk_scan_logo calls
+  // other entry points.
+  mutable std::recursive_mutex mu;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -52,6 +57,7 @@ struct amtk_ctx {
   cudaEvent_t ev_done[2] = { nullptr, nullptr };
   int sm_count = 0;
   int64_t launches = 0;
+  long long h2d_bytes_last = 0;             // payload bytes the last host-clip call copied host->device
   // scratch (grown on demand, reused across calls)
   void* scratch = nullptr; size_t scratch_bytes = 0;       // per-pixel scores
   void* stage[2] = { nullptr, nullptr }; size_t stage_bytes = 0;   // device staging of host clips
@@ -69,6 +75,14 @@ struct amtk_ctx {
     int comb_ws_stages = 2;  // ring slots per warp stream
     int comb_ws = 1;        // 1: round-2 warp-stream kernel for 8-bit clips (comb_stream.cuh); 0: round-1 CTA-ring kernel
   } knobs;
+  // cached launch plan of the streaming comb kernel: work items on the device + occupancy, keyed by geometry and range
+  struct CombPlan {
+    bool valid = false;
+    int wY = 0, hY = 0, wC = 0, hC = 0, nf = 0, f0 = 0, R = 0, item = 0, ctas = 0;
+    void* dev = nullptr; size_t cap = 0;      // [items][CombSegment] + queue counter
+    int nitems = 0; size_t q_off = 0;
+    int occ = 0; const void* occ_kernel = nullptr;
+  } plan;
   // optional per-launch timing of the dominant (comb) kernel with CUDA events on the launching stream
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;   // recorded, not yet resolved

@@ -125,6 +125,7 @@ struct EraseJob {
   int pitchY, pitchUV;           // ELEMENTS
   int frame0, nframes;
   int w, h, logUVx, logUVy, imgx, imgy;
+  int uvparity;                  // ((imgy / 2) % 2) of the logo's REAL frame position (the clip may be an ROI-only staging copy)
   const float *aY, *bY, *aU, *bU, *aV, *bV;
   const float* fades;            // [nframes][2] fadeT, fadeB (device)
   float maxv;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) erase_logo_kernel(const EraseJob j) {
   pixel_t* fr = reinterpret_cast<pixel_t*>(j.base + (long long)(j.frame0 + f) * j.frame_stride);
   const int wc = j.w >> j.logUVx, hc = j.h >> j.logUVy, ny = j.w * j.h, nc = wc * hc;
   const bool frame_mode = (fadeT == fadeB);          // :1374
-  const int uvparity = ((j.imgy / 2) % 2);           // :1385
+  const int uvparity = j.uvparity;                   // :1385
   for (int i = threadIdx.x; i < ny + 2 * nc; i += blockDim.x) {
     pixel_t* p; float a, b, fade;
     if (i < ny) {

@@ -11,8 +11,10 @@
  *     message for the calling thread (the reference: `return false` after ctx->setError(); text fetched with
  *     AMTContext_GetError()).
  *   - handles are opaque, owned by the caller, released with the matching *_destroy().
- *   - a context is bound to ONE CUDA device and ONE stream; calls on distinct contexts may run concurrently
- *     (the reference filters answer CACHE_GET_MTMODE with MT_NICE_FILTER, LogoScan.hpp:1220-1225,1500-1505).
+ *   - a context is bound to ONE CUDA device and ONE stream; calls on distinct contexts run concurrently, calls on the
+ *     SAME context from several host threads are safe and serialise on the context (the reference filters answer
+ *     CACHE_GET_MTMODE with MT_NICE_FILTER, LogoScan.hpp:1220-1225,1500-1505: AviSynth may call GetFrame from several
+ *     Prefetch threads at once).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
  */
 #ifndef AMTK_B200_H
@@ -44,6 +46,9 @@ AMTK_API void amtk_ctx_destroy(amtk_ctx* ctx);
 AMTK_API int amtk_ctx_synchronize(amtk_ctx* ctx);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 AMTK_API int64_t amtk_ctx_launch_count(const amtk_ctx* ctx);
+/* payload bytes the last call on a HOST clip copied host->device (whole frames for the combing pass, only the logo /
+ * scan rectangle rows for the logo entry points -- what the reference reads there, LogoScan.hpp:1559-1566) */
+AMTK_API int64_t amtk_ctx_last_h2d_bytes(const amtk_ctx* ctx);
 
 /* Per-launch timing of the dominant streaming kernel (comb) with CUDA events recorded on the context's stream
  * around each launch; get() synchronizes the stream, returns the accumulated milliseconds and launch count. */

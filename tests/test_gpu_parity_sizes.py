@@ -162,3 +162,84 @@ def test_logo_outlives_its_context(native_lib):
     assert np.array_equal(_bits(a), _bits(b))
     del logo                                                            # destroyed after both contexts are gone
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("bits", [8, 10])
+def test_host_clips_upload_only_the_roi(ctx, oracle, bits):
+    """Host-buffer calls of the logo entry points move only the logo / scan rectangle over PCIe and
+    return exactly what the device-resident call returns -- odd alignments included (imgx not a multiple of 16 or 32)."""
+    w, h, n = 416, 240, 23
+    for (imgx, imgy, lw, lh) in ((150, 34, 64, 48), (20, 0, 70, 40), (416 - 64, 240 - 64, 64, 64), (2, 190, 48, 50)):
+        lg = synth.make_logo(lw, lh, seed=3)
+        f8 = synth.make_frames(11, n, w, h, device="cuda", logo=lg, imgx=imgx, imgy=imgy, logo_period=12)
+        if bits == 8:
+            fr = f8
+        else:
+            fr = (f8.to(torch.int32) * 4 + (f8.to(torch.int32) & 3)).to(torch.int16).contiguous()
+        raw = ab.Logo.create(lg["data"], lw, lh, w, h, imgx, imgy)
+        de, top, bot = raw.deint().create_mask(0.35), raw.field(0).create_mask(0.35), raw.field(1).create_mask(0.35)
+        dclip = ab.yv12_clip(fr, w, h, n, True, bits)
+        host = fr.cpu().numpy()
+        hclip = ab.yv12_clip(host, w, h, n, False, bits)
+        full = host.nbytes
+        s_dev = ctx.scan_frames(dclip, [de]).cpu().numpy()
+        s_host = ctx.scan_frames(hclip, [de])
+        assert np.array_equal(_bits(s_dev), _bits(s_host))
+        assert 0 < ctx.last_h2d_bytes < full // 4, (ctx.last_h2d_bytes, full)
+        a_dev = ctx.analyze_frames(dclip, de, top, bot, 3, 17).cpu().numpy()
+        a_host = ctx.analyze_frames(hclip, de, top, bot, 3, 17)
+        assert np.array_equal(_bits(a_dev), _bits(a_host))
+        fades = np.arange(0, 20, dtype=np.float32) * np.float32(0.1)
+        e_dev = ctx.eval_fades(dclip, de, fades).cpu().numpy()
+        e_host = ctx.eval_fades(hclip, de, fades)
+        assert np.array_equal(_bits(e_dev), _bits(e_host))
+        # in-place erase on host frames == in-place erase in HBM (8- and 16-bit)
+        fd = np.stack([np.linspace(0, 1, n), np.linspace(1, 0, n)], axis=1).astype(np.float32)
+        fd[5] = (0.5, 0.5)
+        work_d = fr.clone()
+        ctx.erase_logo(ab.yv12_clip(work_d, w, h, n, True, bits), raw, fd)
+        work_h = host.copy()
+        ctx.erase_logo(ab.yv12_clip(work_h, w, h, n, False, bits), raw, fd)
+        assert np.array_equal(work_d.cpu().numpy(), work_h) and not np.array_equal(work_h, host)
+        if bits == 8:
+            sx, sy = imgx & ~1, imgy & ~1
+            sw, sh = min(lw, w - sx) & ~1, min(lh, h - sy) & ~1
+            a1, a2 = ctx.logo_scan(sw, sh, 12), ctx.logo_scan(sw, sh, 12)
+            v1 = a1.add_frames(dclip, sx, sy)
+            v2 = a2.add_frames(hclip, sx, sy)
+            assert np.array_equal(v1, v2) and np.array_equal(a1.sums(), a2.sums())
+
+
+def test_one_context_from_two_threads(ctx, oracle):
+    """MT_NICE_FILTER: AviSynth may call GetFrame of one filter from several Prefetch threads.  Two host threads hammer ONE
+    context with 1- and 2-frame calls (ctypes releases the GIL); every result equals the serial run."""
+    import threading
+    w, h, n = 256, 128, 24
+    lg = synth.make_logo(64, 64)
+    fr = synth.make_frames(40, n, w, h, device="cuda", logo=lg, imgx=160, imgy=32, logo_period=12)
+    logo = ab.Logo.create(lg["data"], 64, 64, w, h, 160, 32).deint().create_mask(0.35)
+    host = fr.cpu().numpy()
+    hclip = ab.yv12_clip(host, w, h, n, False)
+    dclip = ab.yv12_clip(fr, w, h, n, True)
+    prm = ab.default_comb_params()
+    ref_s = ctx.scan_frames(dclip, [logo]).cpu().numpy()
+    ref_c = ctx.comb_frames(dclip, prm).cpu().numpy()
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(6):
+                for i in range(tid, n, 2):
+                    s = ctx.scan_frames(hclip, [logo], i, 1)
+                    if not np.array_equal(_bits(s[0]), _bits(ref_s[i])):
+                        errors.append(("scan", tid, i))
+                    c = ctx.comb_frames(hclip, prm, i, 1)
+                    if not np.array_equal(c[0], ref_c[i]):
+                        errors.append(("comb", tid, i))
+        except Exception as e:          # noqa
+            errors.append(("exc", tid, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors[:5]
