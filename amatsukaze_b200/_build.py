@@ -73,6 +73,24 @@ def build_host_test(force=False):
     return HOST_TEST
 
 
+PIPELINE_TEST = os.path.join(PKG, "..", "tests", "cpp", "test_pipeline")
+
+
+def build_pipeline_test(force=False):
+    """tests/cpp/test_pipeline: multi-pass driver, ingest semantics and device frames on a real device."""
+    src = os.path.join(PKG, "..", "tests", "cpp", "test_pipeline.cpp")
+    deps = [src, os.path.join(PKG, "host", "filters.hpp"), os.path.join(PKG, "host", "avs_compat.h"), LIB]
+    if (not force and os.path.exists(PIPELINE_TEST) and all(os.path.getmtime(PIPELINE_TEST) >= os.path.getmtime(d) for d in deps)):
+        return PIPELINE_TEST
+    cmd = ["g++", "-std=c++17", "-O2", "-o", PIPELINE_TEST, src, "-L" + LIBDIR, "-lamtk_b200",
+           "-Wl,-rpath,$ORIGIN/../../amatsukaze_b200/lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("pipeline test build failed")
+    return PIPELINE_TEST
+
+
 HOST_ONLY_TEST = os.path.join(PKG, "..", "tests", "cpp", "test_host_only")
 
 

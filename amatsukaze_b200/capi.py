@@ -62,6 +62,7 @@ SIGNATURES = [
     ("amtk_device_free", None, [V, V]),
     ("amtk_memcpy_h2d", C.c_int, [V, V, V, C.c_size_t]),
     ("amtk_memcpy_d2h", C.c_int, [V, V, V, C.c_size_t]),
+    ("amtk_memcpy_d2d", C.c_int, [V, V, V, C.c_size_t]),
     ("amtk_logo_create", C.c_int, [V, c_float_p] + [C.c_int] * 8 + [VP]),
     ("amtk_logo_load", C.c_int, [V, C.c_char_p, VP, V]),
     ("amtk_logo_save", C.c_int, [V, C.c_char_p, C.c_char_p, C.c_int]),
@@ -87,6 +88,8 @@ SIGNATURES = [
     ("amtk_weave_frames", C.c_int, [V, C.POINTER(ClipDesc), C.POINTER(ClipDesc), C.c_int, c_i32_p, c_i32_p, C.c_int, C.c_int]),
     ("amtk_erase_logo_frames", C.c_int, [V, C.POINTER(ClipDesc), V, C.c_int, C.c_int, c_float_p]),
     ("amtk_calc_fade2", None, [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]),
+    ("amtk_calc_fade2_index", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("amtk_calc_fade2_records", None, [c_float_p, c_float_p, c_float_p]),
 ]
 
 _lib = None

@@ -818,6 +818,13 @@ int amtk_memcpy_h2d(amtk_ctx* c, void* dst, const void* src, size_t bytes) {
   AMTK_CUDA(cudaStreamSynchronize(c->stream));
   return 1;
 }
+int amtk_memcpy_d2d(amtk_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c || !dst || !src) AMTK_FAIL("amtk_memcpy_d2d: null argument");
+  DevSelect ds(c); if (!ds.ok) return 0;
+  AMTK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  AMTK_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}
 int amtk_memcpy_d2h(amtk_ctx* c, void* dst, const void* src, size_t bytes) {
   if (!c || !dst || !src) AMTK_FAIL("amtk_memcpy_d2h: null argument");
   DevSelect ds(c); if (!ds.ok) return 0;
@@ -1374,5 +1381,7 @@ int amtk_weave_frames(amtk_ctx* ctx, const amtk_clip* src, const amtk_clip* dst,
 void amtk_calc_fade2(const float* records, int num_records, int num_frames, int n, float* ft, float* fb) {
   amtk::calc_fade2(records, num_records, num_frames, n, ft, fb);
 }
+int amtk_calc_fade2_index(int num_records, int num_frames, int n, int i) { return amtk::calc_fade2_index(num_records, num_frames, n, i); }
+void amtk_calc_fade2_records(const float* rec9, float* ft, float* fb) { amtk::calc_fade2_records(rec9, ft, fb); }
 
 }  // extern "C"

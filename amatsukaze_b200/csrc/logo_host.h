@@ -66,5 +66,7 @@ bool scan_finalize(const double* sums, int nframes, int scanw, int scanh, int lo
 
 // AMTEraseLogo::CalcFade2 (LogoScan.hpp:1263-1315)
 void calc_fade2(const float* records, int num_records, int num_frames, int n, float* fadeT, float* fadeB);
+int calc_fade2_index(int num_records, int num_frames, int n, int i);
+void calc_fade2_records(const float* rec9, float* fadeT, float* fadeB);
 
 }  // namespace amtk

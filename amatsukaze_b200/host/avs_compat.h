@@ -27,7 +27,10 @@
 struct amtk_ctx;
 
 enum { PLANAR_Y = 1 << 0, PLANAR_U = 1 << 1, PLANAR_V = 1 << 2 };
-enum { CACHE_GET_MTMODE = 509 };                       // only the request the reference's filters answer
+enum { CACHE_GET_MTMODE = 509,                         // the requests the reference's filters answer ...
+       CACHE_GET_DEV_TYPE = 518,                       // ... plus AviSynthNeo's device hooks (include/avisynth.h:1112-1113):
+       CACHE_GET_CHILD_DEV_TYPE = 519 };               // which device a filter returns frames on / accepts frames from
+enum AvsDeviceType { DEV_TYPE_NONE = 0, DEV_TYPE_CPU = 1, DEV_TYPE_CUDA = 2, DEV_TYPE_ANY = 0xFFFF };   // include/avisynth.h:137-141
 enum MtMode { MT_INVALID = 0, MT_NICE_FILTER = 1, MT_MULTI_INSTANCE = 2, MT_SERIALIZED = 3 };
 
 struct AvisynthError {                                  // thrown by IScriptEnvironment::ThrowError
@@ -52,13 +55,34 @@ struct VideoInfo {
   int BytesFromPixels(int pixels) const { return pixel_type == CS_BGR32 ? pixels * 4 : pixels * ComponentSize(); }
 };
 
-// One frame in host memory: planar Y,U,V (or a single packed plane for CS_BGR32), rows 64-byte aligned.
+// One frame: planar Y,U,V (or a single packed plane for CS_BGR32).  Either in host memory (rows 64-byte aligned, owned)
+// or -- the AviSynthNeo DEV_TYPE_CUDA case, include/avisynth.h:1651-1652 NewVideoFrame(vi, device) -- a VIEW of memory in
+// HBM (IsDevice(): the pointers returned by GetReadPtr/GetWritePtr are device pointers; `owner` keeps the allocation
+// alive).  Frame properties (SetProperty/GetProperty, include/avisynth.h:1009-1017) carry FrameType etc.
 class VideoFrame {
   std::vector<uint8_t> buf_;
+  uint8_t* dev_ = nullptr;                 // non-null: device frame (view)
+  size_t dev_bytes_ = 0;
+  std::shared_ptr<void> owner_;
+  std::map<std::string, double> props_;
   int pitch_[3] = { 0, 0, 0 }, rowsize_[3] = { 0, 0, 0 }, height_[3] = { 0, 0, 0 };
   size_t off_[3] = { 0, 0, 0 };
   static int idx(int plane) { return plane == PLANAR_U ? 1 : (plane == PLANAR_V ? 2 : 0); }
 public:
+  // device view: tightly described by per-plane offsets and pitches inside [base, base + bytes)
+  VideoFrame(const VideoInfo& vi, uint8_t* dev_base, size_t bytes, const size_t off[3], const int pitch[3], std::shared_ptr<void> owner)
+      : dev_(dev_base), dev_bytes_(bytes), owner_(owner) {
+    for (int p = 0; p < 3; ++p) {
+      const int w = p ? vi.width >> 1 : vi.width, h = p ? vi.height >> 1 : vi.height;
+      rowsize_[p] = vi.BytesFromPixels(w); pitch_[p] = pitch[p]; height_[p] = h; off_[p] = off[p];
+    }
+  }
+  bool IsDevice() const { return dev_ != nullptr; }
+  void Rebase(uint8_t* dev_base, std::shared_ptr<void> owner) { dev_ = dev_base; owner_ = owner; }   // same geometry, other memory
+  void SetProperty(const char* key, double v) { props_[key] = v; }
+  double GetProperty(const char* key, double def) const { auto it = props_.find(key); return it == props_.end() ? def : it->second; }
+  int GetProperty(const char* key, int def) const { auto it = props_.find(key); return it == props_.end() ? def : (int)it->second; }
+  void CopyPropertiesFrom(const VideoFrame& o) { props_ = o.props_; }
   explicit VideoFrame(const VideoInfo& vi) {
     const int planes = vi.IsPlanar() ? 3 : 1;
     size_t total = 0;
@@ -75,11 +99,11 @@ public:
   int GetPitch(int plane = PLANAR_Y) const { return pitch_[idx(plane)]; }
   int GetRowSize(int plane = PLANAR_Y) const { return rowsize_[idx(plane)]; }
   int GetHeight(int plane = PLANAR_Y) const { return height_[idx(plane)]; }
-  const uint8_t* GetReadPtr(int plane = PLANAR_Y) const { return buf_.data() + off_[idx(plane)]; }
-  uint8_t* GetWritePtr(int plane = PLANAR_Y) { return buf_.data() + off_[idx(plane)]; }
+  const uint8_t* GetReadPtr(int plane = PLANAR_Y) const { return Base() + off_[idx(plane)]; }
+  uint8_t* GetWritePtr(int plane = PLANAR_Y) { return const_cast<uint8_t*>(Base()) + off_[idx(plane)]; }
   size_t GetOffset(int plane) const { return off_[idx(plane)]; }
-  const uint8_t* Base() const { return buf_.data(); }
-  size_t TotalBytes() const { return buf_.size() - 64; }
+  const uint8_t* Base() const { return dev_ ? dev_ : buf_.data(); }
+  size_t TotalBytes() const { return dev_ ? dev_bytes_ : buf_.size() - 64; }
 };
 typedef std::shared_ptr<VideoFrame> PVideoFrame;
 
@@ -151,10 +175,21 @@ public:
   }
   virtual PVideoFrame NewVideoFrame(const VideoInfo& vi) { return std::make_shared<VideoFrame>(vi); }
   virtual bool MakeWritable(PVideoFrame* pvf) {
+    if ((*pvf)->IsDevice()) return MakeWritableDevice(pvf);
     if (pvf->use_count() == 1) return false;
     *pvf = std::make_shared<VideoFrame>(**pvf);         // full-frame copy, as AviSynth does (LogoScan.hpp:1347)
     return true;
   }
+  // device frames: a private HBM copy (device-to-device), provided by the binding layer (filters.hpp)
+  std::function<bool(PVideoFrame*)> MakeWritableDevice = [](PVideoFrame*) { return false; };
+  // AviSynthNeo: which device the consumer of this environment's frames runs on (INeoEnv::GetDeviceType,
+  // include/avisynth.h:1700).  DEV_TYPE_CUDA lets device-resident sources hand out zero-copy frame views.
+  virtual AvsDeviceType GetDeviceType() const { return dev_type_; }
+  void SetDeviceType(AvsDeviceType t) { dev_type_ = t; }
+  // Clips that outlive one script environment (AMTFilterSource builds a fresh environment per pass,
+  // FilteredSource.hpp:519-523; the decoded clip stays resident in HBM across passes through this table).
+  std::map<std::string, std::shared_ptr<IClip>>* SharedClips() { return shared_clips_; }
+  void SetSharedClips(std::map<std::string, std::shared_ptr<IClip>>* m) { shared_clips_ = m; }
   // name, parameter spec ("cs[maskratio]i" ...), factory, user data -- Amatsukaze.cpp:55-63
   virtual void AddFunction(const char* name, const char* params, ApplyFunc apply, void* user_data) {
     funcs_[name] = Func{ params, apply, user_data };
@@ -169,6 +204,7 @@ public:
   // script variables (AMT_SOURCE, AMT_TMP, AMT_PASS, AMT_DEV ... FilteredSource.hpp:530-540)
   virtual bool SetVar(const char* name, const AVSValue& v) { vars_[name] = v; return true; }
   virtual AVSValue GetVarDef(const char* name, const AVSValue& def = AVSValue()) { auto it = vars_.find(name); return it == vars_.end() ? def : it->second; }
+  virtual AVSValue GetVar(const char* name) { auto it = vars_.find(name); if (it == vars_.end()) ThrowError("Script error: no variable named '%s'", name); return it->second; }
   // device binding: analogue of INeoEnv::GetDevice/GetDeviceStream (include/avisynth.h:1698-1706)
   virtual amtk_ctx* GetAmtkContext() { return amtk_; }
   void SetAmtkContext(amtk_ctx* c) { amtk_ = c; }
@@ -177,6 +213,8 @@ private:
   std::map<std::string, Func> funcs_;
   std::map<std::string, AVSValue> vars_;
   amtk_ctx* amtk_ = nullptr;
+  AvsDeviceType dev_type_ = DEV_TYPE_CPU;
+  std::map<std::string, std::shared_ptr<IClip>>* shared_clips_ = nullptr;
 };
 typedef IScriptEnvironment IScriptEnvironment2;
 

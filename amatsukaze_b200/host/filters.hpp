@@ -15,6 +15,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <ctime>
 #include <numeric>
 #include <regex>
 #include <stdexcept>
@@ -47,88 +48,251 @@ public:
   virtual bool GetDeviceClip(amtk_clip* out) = 0;
 };
 
-inline amtk_clip HostFrameClip(const PVideoFrame& f, const VideoInfo& vi) {     // one CPU frame as a 1-frame host clip
+inline amtk_clip HostFrameClip(const PVideoFrame& f, const VideoInfo& vi) {     // one frame (CPU, or a device view) as a 1-frame clip
   amtk_clip c; memset(&c, 0, sizeof(c));
   c.base = f->Base(); c.frame_stride = (int64_t)((f->TotalBytes() + 15) & ~(size_t)15);
   c.off_u = (int64_t)f->GetOffset(PLANAR_U); c.off_v = (int64_t)f->GetOffset(PLANAR_V);
   c.width = vi.width; c.height = vi.height; c.pitch_y = f->GetPitch(PLANAR_Y); c.pitch_uv = f->GetPitch(PLANAR_U);
   c.log_uvx = c.log_uvy = 1; c.bytes_per_sample = vi.ComponentSize(); c.bits_per_sample = vi.BitsPerComponent();
-  c.num_frames = 1; c.on_device = 0;
+  c.num_frames = 1; c.on_device = f->IsDevice() ? 1 : 0;
   return c;
+}
+
+// Binds a script environment to a device context: frames made writable on the device get a private HBM copy.
+inline void BindDevice(IScriptEnvironment* env, amtk_ctx* ctx, AvsDeviceType consumer = DEV_TYPE_CPU) {
+  env->SetAmtkContext(ctx);
+  env->SetDeviceType(consumer);
+  env->MakeWritableDevice = [env, ctx](PVideoFrame* pvf) -> bool {
+    const PVideoFrame& f = *pvf;
+    void* p = nullptr;
+    if (!amtk_device_alloc(ctx, f->TotalBytes(), &p)) env->ThrowError("%s", amtk_last_error());
+    std::shared_ptr<void> own(p, [ctx](void* q) { amtk_device_free(ctx, q); });
+    if (!amtk_memcpy_d2d(ctx, p, f->Base(), f->TotalBytes())) env->ThrowError("%s", amtk_last_error());
+    PVideoFrame w = std::make_shared<VideoFrame>(*f);     // copies geometry + properties, then re-points at the new memory
+    w->Rebase(static_cast<uint8_t*>(p), own);
+    *pvf = w;
+    return true;
+  };
 }
 
 namespace av {
 
+// Picture structure of a decoded frame (StreamUtils.hpp:577-586) and the source-frame list built from it
+// (StreamReform.hpp:145-154,874-904): which decoded picture feeds which OUTPUT frame, and whether the output frame is
+// half a frame period late (bottom-field-first pictures), in which case its top field comes from the PREVIOUS decoded
+// picture (AMTSource.hpp:524-551 OnFrameDecoded).
+enum PICTURE_TYPE { PIC_FRAME = 0, PIC_FRAME_DOUBLING, PIC_FRAME_TRIPLING, PIC_TFF, PIC_BFF, PIC_TFF_RFF, PIC_BFF_RFF, MAX_PIC_TYPE };
+
+struct FilterSourceFrame {
+  bool halfDelay;
+  int decoded;               // index of the decoded picture (the reference keys this by framePTS)
+  double pts;                // in frame periods (the reference: 90 kHz clock)
+};
+
+inline std::vector<FilterSourceFrame> MakeFilterSourceFrames(const std::vector<uint8_t>& pics) {   // StreamReform.hpp:874-904
+  std::vector<FilterSourceFrame> list;
+  for (int d = 0; d < (int)pics.size(); ++d) {
+    FilterSourceFrame f{ false, d, (double)list.size() };
+    switch (pics[d]) {
+      case PIC_FRAME: case PIC_TFF: case PIC_TFF_RFF: list.push_back(f); break;
+      case PIC_FRAME_DOUBLING: list.push_back(f); f.pts += 1; list.push_back(f); break;
+      case PIC_FRAME_TRIPLING: list.push_back(f); f.pts += 1; list.push_back(f); f.pts += 1; list.push_back(f); break;
+      case PIC_BFF: f.halfDelay = true; f.pts -= 0.5; list.push_back(f); break;
+      case PIC_BFF_RFF: f.halfDelay = true; f.pts -= 0.5; list.push_back(f); f.halfDelay = false; f.pts += 1; list.push_back(f); break;
+      default: list.push_back(f); break;
+    }
+  }
+  return list;
+}
+
+// Field plan of every output frame: (top, bottom) decoded-picture indices, exactly what OnFrameDecoded + GetFrame produce
+// (AMTSource.hpp:524-551,721-780): no delay -> MakeFrame(cur, cur); halfDelay -> MakeFrame(prev, cur) when the previous
+// decoded picture exists, otherwise no frame is made and GetFrame serves the next cached frame (ForceGetFrame's
+// lower_bound, :567-577) -- an output frame without its own picture takes the plan of the next one that has.
+inline void MakeFieldPlan(const std::vector<FilterSourceFrame>& frames, std::vector<int32_t>& top, std::vector<int32_t>& bottom) {
+  const int n = (int)frames.size();
+  top.assign(n, -1); bottom.assign(n, -1);
+  for (int k = 0; k < n; ++k) {
+    const int d = frames[k].decoded;
+    if (!frames[k].halfDelay) { top[k] = bottom[k] = d; }
+    else if (d > 0) { top[k] = d - 1; bottom[k] = d; }
+  }
+  int next_t = -1, next_b = -1;
+  for (int k = n - 1; k >= 0; --k) {                       // ForceGetFrame: first cached frame at or after k ...
+    if (top[k] >= 0) { next_t = top[k]; next_b = bottom[k]; }
+    else { top[k] = next_t; bottom[k] = next_b; }
+  }
+  for (int k = 0; k < n; ++k)                               // ... or, past the last one, the last cached frame
+    if (top[k] < 0) { top[k] = k ? top[k - 1] : 0; bottom[k] = k ? bottom[k - 1] : 0; }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // AMTSource: frame provider.  The reference decodes MPEG2/H.264 with FFmpeg into CPU frames on demand
-// (AMTSource.hpp:585-780); decode is out of scope here, so the source is a raw planar clip file (the stand-in for
-// the `amts%d.dat` artefact, AMTSource.hpp:835-871) that is uploaded once and stays resident in HBM.
-// File: "AMTSRAW1" + int32 {width,height,bits,num_frames,fps_num,fps_den} + tightly packed planar 4:2:0 frames.
+// (AMTSource.hpp:585-780); decode is out of scope here, so the source is a file of DECODED pictures (the stand-in for the
+// `amts%d.dat` artefact, AMTSource.hpp:835-871) that is uploaded ONCE and stays resident in HBM.  Everything after the
+// decoder is reproduced: the picture-structure -> source-frame list, the half-delay field weave (MergeField on the
+// device, amtk_weave_frames), NV12 chroma split, the FrameType frame property, GetParity, MT mode.
+//   "AMTSRAW1" + int32 {width,height,bits,num_frames,fps_num,fps_den} + planar 4:2:0 frames            (all PIC_FRAME)
+//   "AMTSRAW2" + the same six int32 + int32 {nv12} + num x {uint8 pic_struct, uint8 pict_type} + decoded pictures
 // ---------------------------------------------------------------------------------------------------------------
 class AMTSource : public IClip, public IDeviceClip {
   VideoInfo vi;
   amtk_ctx* ctx;
-  std::vector<uint8_t> host;          // CPU copy (serves GetFrame)
-  void* dev = nullptr;                // HBM copy (serves batched filters)
+  std::vector<uint8_t> host;          // CPU copy of the OUTPUT frames, made lazily (only CPU consumers need it)
+  bool host_valid = false;
+  std::shared_ptr<void> dev;          // HBM: output frames (what filters read)
+  std::vector<uint8_t> pict_type;     // per OUTPUT frame: AV_PICTURE_TYPE of the picture that supplies its top field
+  std::vector<FilterSourceFrame> frames_;
   bool interlaced = true;
   size_t ysz() const { return (size_t)vi.width * vi.height * vi.ComponentSize(); }
   size_t csz() const { return (size_t)(vi.width / 2) * (vi.height / 2) * vi.ComponentSize(); }
   size_t fsz() const { return ysz() + 2 * csz(); }
+  static std::shared_ptr<void> DevAlloc(amtk_ctx* ctx, size_t bytes, IScriptEnvironment* env) {
+    void* p = nullptr;
+    amtk_check(amtk_device_alloc(ctx, bytes, &p), env);
+    return std::shared_ptr<void>(p, [ctx](void* q) { amtk_device_free(ctx, q); });
+  }
+  amtk_clip Desc(void* base, int nframes, bool nv12 = false) const {
+    amtk_clip c; memset(&c, 0, sizeof(c));
+    c.base = base; c.frame_stride = (int64_t)fsz(); c.off_u = (int64_t)ysz(); c.off_v = (int64_t)(ysz() + csz());
+    c.width = vi.width; c.height = vi.height; c.pitch_y = vi.width * vi.ComponentSize();
+    c.pitch_uv = (nv12 ? vi.width : vi.width / 2) * vi.ComponentSize();
+    c.log_uvx = c.log_uvy = 1; c.bytes_per_sample = vi.ComponentSize(); c.bits_per_sample = vi.BitsPerComponent();
+    c.num_frames = nframes; c.on_device = 1;
+    return c;
+  }
+  void EnsureHost(IScriptEnvironment* env) {
+    if (host_valid) return;
+    host.resize(fsz() * vi.num_frames);
+    amtk_check(amtk_memcpy_d2h(ctx, host.data(), dev.get(), host.size()), env);
+    host_valid = true;
+  }
 public:
   AMTSource(const tstring& path, IScriptEnvironment* env) : ctx(env->GetAmtkContext()) {
     FILE* fp = fopen(path.c_str(), "rb");
     if (!fp) env->ThrowError("AMTSource: failed to open %s", path.c_str());
-    char magic[8]; int32_t h[6];
-    if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, "AMTSRAW1", 8) != 0 || fread(h, 4, 6, fp) != 6) { fclose(fp); env->ThrowError("AMTSource: bad header in %s", path.c_str()); }
-    vi.width = h[0]; vi.height = h[1]; vi.num_frames = h[3]; vi.fps_numerator = (unsigned)h[4]; vi.fps_denominator = (unsigned)h[5];
+    char magic[8]; int32_t h[6]; int32_t nv12 = 0;
+    if (fread(magic, 1, 8, fp) != 8 || (memcmp(magic, "AMTSRAW1", 8) != 0 && memcmp(magic, "AMTSRAW2", 8) != 0) || fread(h, 4, 6, fp) != 6) {
+      fclose(fp); env->ThrowError("AMTSource: bad header in %s", path.c_str());
+    }
+    const bool v2 = magic[7] == '2';
+    const int ndec = h[3];
+    vi.width = h[0]; vi.height = h[1]; vi.fps_numerator = (unsigned)h[4]; vi.fps_denominator = (unsigned)h[5];
     switch (h[2]) {                                       // AMTSource.hpp:428-442
       case 8: vi.pixel_type = VideoInfo::CS_YV12; break;
       case 10: vi.pixel_type = VideoInfo::CS_YUV420P10; break;
       case 12: vi.pixel_type = VideoInfo::CS_YUV420P12; break;
       default: fclose(fp); env->ThrowError("AMTSource: unsupported bit depth %d", h[2]);
     }
-    host.resize(fsz() * vi.num_frames);
-    const bool ok = fread(host.data(), 1, host.size(), fp) == host.size();
+    std::vector<uint8_t> pics((size_t)ndec, (uint8_t)PIC_FRAME), ptype((size_t)ndec, 1);
+    if (v2) {
+      std::vector<uint8_t> meta((size_t)ndec * 2);
+      if (fread(&nv12, 4, 1, fp) != 1 || fread(meta.data(), 1, meta.size(), fp) != meta.size()) { fclose(fp); env->ThrowError("AMTSource: truncated file %s", path.c_str()); }
+      for (int d = 0; d < ndec; ++d) { pics[d] = meta[2 * d]; ptype[d] = meta[2 * d + 1]; if (pics[d] >= MAX_PIC_TYPE) { fclose(fp); env->ThrowError("AMTSource: bad picture structure"); } }
+    }
+    if (!ctx) { fclose(fp); env->ThrowError("AMTSource: no device bound to the script environment"); }
+    // decoded pictures: pinned staging -> HBM
+    const size_t dec_bytes = fsz() * (size_t)ndec;
+    void* pinned = nullptr;
+    amtk_check(amtk_host_alloc(std::max<size_t>(dec_bytes, 16), &pinned), env);
+    const bool ok = fread(pinned, 1, dec_bytes, fp) == dec_bytes;
     fclose(fp);
-    if (!ok) env->ThrowError("AMTSource: truncated file %s", path.c_str());
-    if (!ctx) env->ThrowError("AMTSource: no device bound to the script environment");
-    amtk_check(amtk_device_alloc(ctx, host.size(), &dev), env);
-    amtk_check(amtk_memcpy_h2d(ctx, dev, host.data(), host.size()), env);
+    if (!ok) { amtk_host_free(pinned); env->ThrowError("AMTSource: truncated file %s", path.c_str()); }
+    std::shared_ptr<void> decoded = DevAlloc(ctx, std::max<size_t>(dec_bytes, 16), env);
+    const int up = amtk_memcpy_h2d(ctx, decoded.get(), pinned, dec_bytes);
+    amtk_host_free(pinned);
+    amtk_check(up, env);
+    frames_ = MakeFilterSourceFrames(pics);
+    vi.num_frames = (int)frames_.size();
+    std::vector<int32_t> top, bottom;
+    MakeFieldPlan(frames_, top, bottom);
+    bool identity = !nv12 && vi.num_frames == ndec;
+    for (int k = 0; k < vi.num_frames && identity; ++k) identity = top[k] == k && bottom[k] == k;
+    if (identity) dev = decoded;                          // progressive / TFF material: the decoded pictures ARE the frames
+    else {                                                // MakeFrame for every output frame, on the device (AMTSource.hpp:357-366)
+      dev = DevAlloc(ctx, fsz() * (size_t)vi.num_frames, env);
+      const amtk_clip src = Desc(decoded.get(), ndec, nv12 != 0), dst = Desc(dev.get(), vi.num_frames);
+      amtk_check(amtk_weave_frames(ctx, &src, &dst, 0, top.data(), bottom.data(), vi.num_frames, nv12 != 0), env);
+    }
+    pict_type.resize(vi.num_frames);
+    for (int k = 0; k < vi.num_frames; ++k) pict_type[k] = ptype[top[k]];          // ret->SetProperty("FrameType", top->pict_type) :369
   }
-  ~AMTSource() { if (dev) amtk_device_free(ctx, dev); }
+
+  const std::vector<FilterSourceFrame>& SourceFrames() const { return frames_; }
 
   PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment* env) override {
     n = std::max(0, std::min(vi.num_frames - 1, n));
-    PVideoFrame f = env->NewVideoFrame(vi);
-    const uint8_t* src = host.data() + fsz() * n;
-    const int planes[3] = { PLANAR_Y, PLANAR_U, PLANAR_V };
-    size_t off = 0;
-    for (int p = 0; p < 3; ++p) {
-      const int rows = f->GetHeight(planes[p]), rb = f->GetRowSize(planes[p]);
-      for (int y = 0; y < rows; ++y) memcpy(f->GetWritePtr(planes[p]) + (size_t)y * f->GetPitch(planes[p]), src + off + (size_t)y * rb, rb);
-      off += (size_t)rows * rb;
+    PVideoFrame f;
+    if (env->GetDeviceType() == DEV_TYPE_CUDA) {          // zero-copy view of the resident frame (AviSynthNeo device frame)
+      const size_t off[3] = { 0, ysz(), ysz() + csz() };
+      const int pitch[3] = { vi.width * vi.ComponentSize(), (vi.width / 2) * vi.ComponentSize(), (vi.width / 2) * vi.ComponentSize() };
+      f = std::make_shared<VideoFrame>(vi, static_cast<uint8_t*>(dev.get()) + fsz() * n, fsz(), off, pitch, dev);
+    } else {
+      EnsureHost(env);
+      f = env->NewVideoFrame(vi);
+      const uint8_t* src = host.data() + fsz() * n;
+      const int planes[3] = { PLANAR_Y, PLANAR_U, PLANAR_V };
+      size_t off = 0;
+      for (int p = 0; p < 3; ++p) {
+        const int rows = f->GetHeight(planes[p]), rb = f->GetRowSize(planes[p]);
+        for (int y = 0; y < rows; ++y) memcpy(f->GetWritePtr(planes[p]) + (size_t)y * f->GetPitch(planes[p]), src + off + (size_t)y * rb, rb);
+        off += (size_t)rows * rb;
+      }
     }
+    f->SetProperty("FrameType", (double)pict_type[n]);
     return f;
   }
-  bool GetDeviceClip(amtk_clip* c) override {
-    memset(c, 0, sizeof(*c));
-    c->base = dev; c->frame_stride = (int64_t)fsz(); c->off_u = (int64_t)ysz(); c->off_v = (int64_t)(ysz() + csz());
-    c->width = vi.width; c->height = vi.height; c->pitch_y = vi.width * vi.ComponentSize(); c->pitch_uv = (vi.width / 2) * vi.ComponentSize();
-    c->log_uvx = c->log_uvy = 1; c->bytes_per_sample = vi.ComponentSize(); c->bits_per_sample = vi.BitsPerComponent();
-    c->num_frames = vi.num_frames; c->on_device = 1;
-    return true;
-  }
-  // device frames edited in place by a batched filter become visible to GetFrame after this
-  void SyncHostFromDevice(IScriptEnvironment* env) { amtk_check(amtk_memcpy_d2h(ctx, host.data(), dev, host.size()), env); }
+  bool GetDeviceClip(amtk_clip* c) override { *c = Desc(dev.get(), vi.num_frames); return true; }
+  // device frames edited in place by a batched filter become visible to CPU GetFrame after this
+  void SyncHostFromDevice(IScriptEnvironment*) { host_valid = false; }
   void __stdcall GetAudio(void*, int64_t, int64_t, IScriptEnvironment*) override {}
   const VideoInfo& __stdcall GetVideoInfo() override { return vi; }
   bool __stdcall GetParity(int) override { return interlaced; }                         // AMTSource.hpp:821-823
-  int __stdcall SetCacheHints(int cachehints, int) override { return cachehints == CACHE_GET_MTMODE ? MT_NICE_FILTER : 0; }   // :825-830
+  int __stdcall SetCacheHints(int cachehints, int) override {                             // :825-830 + Neo device hooks
+    if (cachehints == CACHE_GET_MTMODE) return MT_NICE_FILTER;
+    if (cachehints == CACHE_GET_DEV_TYPE) return DEV_TYPE_CPU | DEV_TYPE_CUDA;
+    return 0;
+  }
 };
 
 inline AVSValue __cdecl CreateAMTSource(AVSValue args, void*, IScriptEnvironment* env) {     // AMTSource.hpp:873-882
-  return AVSValue(PClip(new AMTSource(args[0].AsString(), env)));        // [filter]s [outqp]b are decode options: ignored
+  // [filter]s [outqp]b are decode options: ignored.  A clip already opened by an earlier pass of the same job is shared.
+  const std::string path = args[0].AsString();
+  if (auto* shared = env->SharedClips()) {
+    auto it = shared->find("AMTSource:" + path);
+    if (it != shared->end()) return AVSValue(it->second);
+    PClip c(new AMTSource(path, env));
+    (*shared)["AMTSource:" + path] = c;
+    return AVSValue(c);
+  }
+  return AVSValue(PClip(new AMTSource(path, env)));
 }
+
+// OnCPU (AviSynthNeo): downloads device frames so that a CPU consumer can read them.
+class OnCPU : public GenericVideoFilter {
+public:
+  explicit OnCPU(PClip c) : GenericVideoFilter(c) {}
+  PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment* env) override {
+    PVideoFrame f = child->GetFrame(n, env);
+    if (!f->IsDevice()) return f;
+    PVideoFrame h = env->NewVideoFrame(vi);
+    std::vector<uint8_t> tmp(f->TotalBytes());
+    amtk_check(amtk_memcpy_d2h(env->GetAmtkContext(), tmp.data(), f->Base(), tmp.size()), env);
+    const int planes[3] = { PLANAR_Y, PLANAR_U, PLANAR_V };
+    for (int p = 0; p < 3; ++p)
+      for (int y = 0; y < h->GetHeight(planes[p]); ++y)
+        memcpy(h->GetWritePtr(planes[p]) + (size_t)y * h->GetPitch(planes[p]),
+               tmp.data() + f->GetOffset(planes[p]) + (size_t)y * f->GetPitch(planes[p]), h->GetRowSize(planes[p]));
+    h->CopyPropertiesFrom(*f);
+    return h;
+  }
+  int __stdcall SetCacheHints(int cachehints, int) override {
+    if (cachehints == CACHE_GET_MTMODE) return MT_NICE_FILTER;
+    if (cachehints == CACHE_GET_DEV_TYPE) return DEV_TYPE_CPU;
+    if (cachehints == CACHE_GET_CHILD_DEV_TYPE) return DEV_TYPE_CUDA | DEV_TYPE_CPU;
+    return 0;
+  }
+};
 
 }  // namespace av
 
@@ -218,22 +382,22 @@ class AMTEraseLogo : public GenericVideoFilter {
   std::vector<int> frameResult;
   LogoHandle logo;
   int mode, maxFadeLength;
+  std::string lastDebugLabel;
 
   void CalcFade2(int n, float& fadeT, float& fadeB, IScriptEnvironment* env) {           // :1263-1315
-    // the 9 records around n sit in at most 3 analyze frames; fetch them through the analyze clip's GetFrame
+    // CalcFade2 looks at nine analyze records around n; they sit in at most three analyze frames (8 records each), which
+    // are fetched through the analyze clip's GetFrame exactly like the reference does -- nothing proportional to the clip
+    // length is allocated or cleared here.
     const int nrec = vi.num_frames;
-    std::vector<float> rec((size_t)nrec * 33, 0.0f);
-    std::vector<char> have((size_t)nblocks(nrec, 8), 0);
+    float rec9[9 * 33];
+    PVideoFrame held; int held_blk = -1;
     for (int i = -4; i <= 4; ++i) {
-      const int nsrc = std::max(0, std::min(vi.num_frames - 1, n + i));
-      const int blk = std::max(0, std::min((int)have.size() - 1, (nsrc + i) >> 3));
-      if (have[blk]) continue;
-      PVideoFrame f = analyzeclip->GetFrame(blk, env);
-      const int cnt = std::min(8, nrec - blk * 8);
-      memcpy(&rec[(size_t)blk * 8 * 33], f->GetReadPtr(), (size_t)cnt * sizeof(LogoAnalyzeFrame));
-      have[blk] = 1;
+      const int src = amtk_calc_fade2_index(nrec, vi.num_frames, n, i);
+      const int blk = src >> 3;
+      if (blk != held_blk) { held = analyzeclip->GetFrame(blk, env); held_blk = blk; }
+      memcpy(rec9 + (size_t)(i + 4) * 33, reinterpret_cast<const LogoAnalyzeFrame*>(held->GetReadPtr()) + (src & 7), sizeof(LogoAnalyzeFrame));
     }
-    amtk_calc_fade2(rec.data(), nrec, vi.num_frames, n, &fadeT, &fadeB);
+    amtk_calc_fade2_records(rec9, &fadeT, &fadeB);
   }
   void CalcFade(int n, float& fadeT, float& fadeB, IScriptEnvironment* env) {            // :1317-1341
     if (frameResult.empty()) { CalcFade2(n, fadeT, fadeB, env); return; }
@@ -287,21 +451,23 @@ public:
     env->MakeWritable(&frame);
     float fades[2];
     CalcFade(n, fades[0], fades[1], env);
-    if (mode != 0) return frame;                          // debug overlay mode of the reference draws text only
-    // one frame through HBM: upload, Delogo kernel in place, download
-    amtk_ctx* ctx = env->GetAmtkContext();
-    const size_t bytes = (frame->TotalBytes() + 15) & ~(size_t)15;
-    void* d = nullptr;
-    amtk_check(amtk_device_alloc(ctx, bytes, &d), env);
+    if (mode != 0) {                       // logo-frame debug mode (:1400-1418): the frame is returned with a text label
+      lastDebugLabel = DebugLabel(fades[0], fades[1]);      // drawn by the reference's DrawText (TextOut.cpp, out of scope); the
+      return frame;                                          // label itself is available through GetDebugLabel()
+    }
+    // The CPU frame is edited in place; the library moves only the three logo rectangles through HBM (Delogo kernel),
+    // with no per-frame device allocation and no full-frame copy.
     amtk_clip c = HostFrameClip(frame, vi);
-    int ok = amtk_memcpy_h2d(ctx, d, frame->Base(), frame->TotalBytes());
-    c.base = d; c.on_device = 1;
-    ok = ok && amtk_erase_logo_frames(ctx, &c, logo.h, 0, 1, fades);
-    ok = ok && amtk_memcpy_d2h(ctx, frame->GetWritePtr(PLANAR_Y), d, frame->TotalBytes());
-    amtk_device_free(ctx, d);
-    amtk_check(ok, env);
+    amtk_check(amtk_erase_logo_frames(env->GetAmtkContext(), &c, logo.h, 0, 1, fades), env);
     return frame;
   }
+  static std::string DebugLabel(float fadeT, float fadeB) {                               // :1404-1414
+    const char* str = (fadeT == fadeB) ? ((fadeT < 0.5) ? "X" : "O") : ((fadeT < fadeB) ? "BTM" : "TOP");
+    char buf[200];
+    snprintf(buf, sizeof(buf), "%s %.1f vs %.1f", str, fadeT, fadeB);
+    return buf;
+  }
+  const std::string& GetDebugLabel() const { return lastDebugLabel; }
   // Batched form for an HBM-resident source: every frame of [first, first+count) erased in place with one launch.
   void EraseInPlace(int first, int count, IScriptEnvironment* env) {
     amtk_clip dc;
@@ -508,18 +674,36 @@ class AMTCombAnalyze : public GenericVideoFilter {
     if (d && d->GetDeviceClip(&dc)) {
       amtk_check(amtk_comb_frames(ctx, &dc, &prm, 0, vi.num_frames, counts.data(), 0), env);
     } else {                                  // generic source: frames are packed pairwise (prev, cur) on the host
-      PVideoFrame prev = child->GetFrame(0, env);
-      for (int n = 0; n < vi.num_frames; ++n) {
-        PVideoFrame cur = n ? child->GetFrame(n, env) : prev;
-        const size_t fb = (cur->TotalBytes() + 15) & ~(size_t)15;
-        std::vector<uint8_t> two(2 * fb);
-        memcpy(two.data(), prev->Base(), prev->TotalBytes()); memcpy(two.data() + fb, cur->Base(), cur->TotalBytes());
-        amtk_clip hc = HostFrameClip(cur, vi);
-        hc.base = two.data(); hc.frame_stride = (int64_t)fb; hc.num_frames = 2;
-        amtk_check(amtk_comb_frames(ctx, &hc, &prm, 1, 1, &counts[(size_t)n * 12], 0), env);
-        if (n == 0) for (int k : { 0, 3, 6, 9 }) counts[k] = 0;       // prev(0) = frame 0 itself
-        prev = cur;
+      // generic IClip: frames are pulled into one (K+1)-frame buffer -- pinned host memory for CPU frames, HBM for device
+      // frames -- and analysed K at a time; slot 0 always holds the frame before the batch (the metric's halo), so no frame
+      // is copied or uploaded twice
+      const int K = 16;
+      PVideoFrame f0 = child->GetFrame(0, env);
+      const bool on_dev = f0->IsDevice();
+      const size_t fb = (f0->TotalBytes() + 15) & ~(size_t)15;
+      void* mem = nullptr;
+      amtk_check(on_dev ? amtk_device_alloc(ctx, (size_t)(K + 1) * fb, &mem) : amtk_host_alloc((size_t)(K + 1) * fb, &mem), env);
+      uint8_t* buf = static_cast<uint8_t*>(mem);
+      auto put = [&](size_t slot, const uint8_t* src, size_t bytes) -> int {
+        if (on_dev) return amtk_memcpy_d2d(ctx, buf + slot * fb, src, bytes);
+        memcpy(buf + slot * fb, src, bytes); return 1;
+      };
+      amtk_clip hc = HostFrameClip(f0, vi);
+      hc.base = buf; hc.frame_stride = (int64_t)fb; hc.num_frames = K + 1;
+      int ok = 1;
+      for (int n0 = 0; n0 < vi.num_frames && ok; n0 += K) {
+        const int cnt = std::min(K, vi.num_frames - n0);
+        const int slot0 = n0 == 0 ? 0 : 1;                  // the first batch starts in slot 0: prev(frame 0) = frame 0 itself
+        for (int k = 0; k < cnt && ok; ++k) {
+          PVideoFrame cur = (n0 + k) ? child->GetFrame(n0 + k, env) : f0;
+          if (cur->IsDevice() != on_dev) { ok = 0; break; }
+          ok = put((size_t)(slot0 + k), cur->Base(), cur->TotalBytes());
+        }
+        ok = ok && amtk_comb_frames(ctx, &hc, &prm, slot0, cnt, &counts[(size_t)n0 * 12], 0);
+        ok = ok && put(0, buf + (size_t)(slot0 + cnt - 1) * fb, fb);        // last frame of this batch = halo of the next
       }
+      if (on_dev) amtk_device_free(ctx, mem); else amtk_host_free(mem);
+      amtk_check(ok, env);
     }
     if (!outpath.empty()) {
       FILE* fp = fopen(outpath.c_str(), "w");
@@ -663,11 +847,7 @@ inline int WriteTelecineFiles(const std::vector<int32_t>& counts, int num_frames
   return film_cycles;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// CMAnalyze (CMAnalyze.hpp:22-317) -- the logo-analysis half only: the constructor runs logoFrame() when logos are
-// configured and exposes getLogoPath().  chapter_exe / join_logo_scp subprocesses, Trim/zone parsing (:319-679) are
-// out of scope (SURVEY section 8).  ConfigWrapper is reduced to the accessors logoFrame() reads.
-// ---------------------------------------------------------------------------------------------------------------
+// ConfigWrapper is reduced to the accessors logoFrame() and AMTFilterSource read.
 struct ConfigWrapper {
   std::vector<tstring> logoPath, eraseLogoPath;          // --logo / --erase-logo (AmatsukazeCLI.hpp:358-366)
   bool looseLogoDetection = false;                       // --loose-logo-detection (:370)
@@ -675,6 +855,13 @@ struct ConfigWrapper {
   const std::vector<tstring>& getLogoPath() const { return logoPath; }
   const std::vector<tstring>& getEraseLogoPath() const { return eraseLogoPath; }
   bool isLooseLogoDetection() const { return looseLogoDetection; }
+  bool noDelogo = false;                                 // --no-delogo
+  int maxFadeLength = 16;                                // --max-fade-length
+  bool isNoDelogo() const { return noDelogo; }
+  int getMaxFadeLength() const { return maxFadeLength; }
+  tstring getAvsTmpPath(int v) const { return tmpDir + "/v" + std::to_string(v) + "-0-0.avstmp"; }             // TranscodeSetting.hpp:875-880 (format, div = 0)
+  tstring getAvsDurationPath(int v) const { return getAvsTmpPath(v) + ".duration.txt"; }                       // :882-885
+  tstring getAvsTimecodePath(int v) const { return getAvsTmpPath(v) + ".timecode.txt"; }                       // :887-890
   tstring getTmpAMTSourcePath(int v) const { return tmpDir + "/amts" + std::to_string(v) + ".dat"; }            // TranscodeSetting.hpp:926-928
   tstring getTmpLogoFramePath(int v, int logoIndex = -1) const {                                               // :934-939
     return tmpDir + "/logof" + std::to_string(v) + (logoIndex == -1 ? std::string() : "-" + std::to_string(logoIndex)) + ".txt";
@@ -682,6 +869,196 @@ struct ConfigWrapper {
 };
 
 struct AviSynthException : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// AMTTelecineDecide: the second pre-process pass.  Reads the counters the first pass left in <AMT_TMP>.combstat.txt and
+// writes <AMT_TMP>.duration.txt / .timecode.txt (consumed by AMTDecimate and readTimecodeFile) on first use; GetFrame
+// hands the source frame through, like every pre-process filter.
+class AMTTelecineDecide : public GenericVideoFilter {
+  tstring base;
+  bool done = false;
+  int film_cycles = -1;
+  void Run(IScriptEnvironment* env) {
+    if (done) return;
+    FILE* fp = fopen((base + ".combstat.txt").c_str(), "r");
+    if (!fp) env->ThrowError("AMTTelecineDecide: pass 1 results missing (%s.combstat.txt)", base.c_str());
+    std::vector<int32_t> counts((size_t)vi.num_frames * 12, 0);
+    size_t got = 0;
+    for (; got < counts.size(); ++got) if (fscanf(fp, "%d", &counts[got]) != 1) break;
+    fclose(fp);
+    if (got != counts.size()) env->ThrowError("AMTTelecineDecide: %s.combstat.txt does not match the clip (%d frames)", base.c_str(), vi.num_frames);
+    film_cycles = WriteTelecineFiles(counts, vi.num_frames, vi.fps_numerator, vi.fps_denominator, base);
+    if (film_cycles < 0) env->ThrowError("AMTTelecineDecide: failed to write %s.duration.txt", base.c_str());
+    done = true;
+  }
+public:
+  AMTTelecineDecide(PClip clip, const tstring& base, IScriptEnvironment*) : GenericVideoFilter(clip), base(base) {}
+  PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment* env) override { Run(env); return child->GetFrame(n, env); }
+  int FilmCycles(IScriptEnvironment* env) { Run(env); return film_cycles; }
+  int __stdcall SetCacheHints(int cachehints, int) override { return cachehints == CACHE_GET_MTMODE ? MT_SERIALIZED : 0; }
+};
+
+// KFMDeint stand-in: the reference's scripts call `dsrc.KFMDeint(mode=.., pass=pass, ..., dev=AMT_DEV, filepath=AMT_TMP)`
+// from the external KFM plugin (Misc.cs:1297-1323).  Only its PASS PROTOCOL is reproduced here, on this repo's combing
+// metric: pass 1 = counters (pre-process), pass 2 = pulldown decision -> duration/timecode files (pre-process),
+// pass 3 = the clip handed to the encoder (AMTFilterSource then appends AMTDecimate because the duration file exists).
+inline AVSValue __cdecl CreateKFMDeint(AVSValue args, void*, IScriptEnvironment* env) {
+  PClip clip = args[0].AsClip();
+  const int pass = args[2].AsInt(0);
+  const tstring base = args[3].AsString("");
+  if (pass == 1) return AVSValue(PClip(new AMTCombAnalyze(clip, base.empty() ? tstring() : base + ".combstat.txt", env)));
+  if (pass == 2) { if (base.empty()) env->ThrowError("KFMDeint: pass 2 needs filepath"); return AVSValue(PClip(new AMTTelecineDecide(clip, base, env))); }
+  return AVSValue(clip);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AMTFilterSource (FilteredSource.hpp:214-300,417-544): the multi-pass filter driver.  Up to four passes; every pass
+// builds a FRESH script environment (InitEnv), defines MakeSource(), sets AMT_SOURCE / AMT_TMP / AMT_PASS / AMT_DEV,
+// runs the main filter script and asks whether it declared itself a pre-process (AMT_PRE_PROC); a pre-process pass is
+// pulled frame by frame and discarded (ReadAllFrames), the first non-pre-process pass is the output.  Afterwards
+// AMTDecimate is appended when the passes left a duration file, and the timecode file is read.
+// AviSynth script text is replaced by a C++ callable with the same contract (reads the AMT_* variables, may set
+// AMT_PRE_PROC, leaves the result in `last`); KFMVfrScript / KFMCfrScript are the two scripts Misc.cs generates.
+// What is new on the B200: the decoded clip is uploaded ONCE -- the environments of all passes share it through
+// SharedClips -- where the reference re-opens and re-decodes the source in every pass (:441-447, InitEnv per pass).
+// ---------------------------------------------------------------------------------------------------------------
+struct EncodeFileKey { int video = 0; };
+typedef std::function<void(IScriptEnvironment*)> FilterScript;
+
+inline void KFMVfrScript(IScriptEnvironment* env) {                                       // Misc.cs:1305-1307,1315-1323
+  const int AMT_PASS = env->GetVar("AMT_PASS").AsInt();
+  static const int sel[3] = { 1, 2, 3 };
+  const int pass = sel[std::max(0, std::min(2, AMT_PASS))];                              // pass = Select(AMT_PASS, 1, 2, 3)
+  env->SetVar("AMT_PRE_PROC", AVSValue(AMT_PASS < 2));
+  env->SetVar("last", env->Invoke("KFMDeint", AVSValue(std::vector<AVSValue>{ env->GetVar("AMT_SOURCE"), AVSValue(4), AVSValue(pass),
+                                  AVSValue(std::string(env->GetVar("AMT_TMP").AsString())), env->GetVar("AMT_DEV") })));
+}
+inline void KFMCfrScript(IScriptEnvironment* env) {                                       // Misc.cs:1311-1313
+  const int AMT_PASS = env->GetVar("AMT_PASS").AsInt();
+  static const int sel[2] = { 1, 3 };
+  const int pass = sel[std::max(0, std::min(1, AMT_PASS))];                              // pass = Select(AMT_PASS, 1, 3)
+  env->SetVar("AMT_PRE_PROC", AVSValue(AMT_PASS < 1));
+  env->SetVar("last", env->Invoke("KFMDeint", AVSValue(std::vector<AVSValue>{ env->GetVar("AMT_SOURCE"), AVSValue(2), AVSValue(pass),
+                                  AVSValue(std::string(env->GetVar("AMT_TMP").AsString())), env->GetVar("AMT_DEV") })));
+}
+
+extern "C" inline const char* __stdcall AvisynthPluginInit3(IScriptEnvironment* env, const AVS_Linkage* const);
+
+class AMTFilterSource {
+public:
+  struct PassInfo { int pass; bool preproc; int frames; double seconds; };
+
+  AMTFilterSource(AMTContext& ctx, const ConfigWrapper& setting, amtk_ctx* device, int gpuIndex, EncodeFileKey key,
+                  const tstring& logopath, FilterScript mainScript, FilterScript postScript = nullptr,
+                  AvsDeviceType consumer = DEV_TYPE_CUDA, FilterScript envHook = nullptr)
+      : ctx(ctx), setting_(setting), device_(device), consumer_(consumer), envHook_(envHook) {
+    try {
+      int pass = 0;
+      for (; pass < 4; ++pass) {                                                         // :232-238
+        if (!FilterPass(pass, gpuIndex, key, logopath, mainScript)) break;
+        ReadAllFrames(pass);
+      }
+      // (after four pre-process passes the reference keeps the environment of the last one as the output, :257-275)
+      if (postScript) { env_->SetVar("AMT_SOURCE", env_->GetVar("last")); postScript(env_.get()); }   // :257-261
+      const tstring durationpath = setting_.getAvsDurationPath(key.video);               // :263-267
+      if (FileExists(durationpath))
+        env_->SetVar("last", env_->Invoke("AMTDecimate", AVSValue(std::vector<AVSValue>{ env_->GetVar("last"), AVSValue(durationpath) })));
+      readTimecode(key);                                                                 // :269
+      filter_ = env_->GetVar("last").AsClip();
+      MakeOutFormat();
+    } catch (const AvisynthError& avserror) {
+      throw AviSynthException(avserror.msg);                                             // :289-295
+    }
+  }
+  const PClip& getClip() const { return filter_; }
+  IScriptEnvironment2* getEnv() const { return env_.get(); }
+  const VideoInfo& getVideoInfo() const { return outvi_; }
+  const std::vector<double>& getTimeCodes() const { return timeCodes_; }
+  int getVfrTimingFps() const { return vfrTimingFps_; }
+  const std::vector<PassInfo>& getPasses() const { return passes_; }
+  int numSourceUploads() const { return (int)shared_.size(); }        // clips opened over ALL passes (1 = uploaded once)
+
+private:
+  AMTContext& ctx;
+  const ConfigWrapper& setting_;
+  amtk_ctx* device_;
+  AvsDeviceType consumer_;
+  FilterScript envHook_;                                // runs at the end of InitEnv (tests: replace AMTSource by a CPU clip)
+  std::unique_ptr<IScriptEnvironment2> env_;
+  std::map<std::string, PClip> shared_;                 // HBM-resident clips shared by the environments of all passes
+  PClip filter_;
+  VideoInfo outvi_;
+  std::vector<double> timeCodes_;
+  int vfrTimingFps_ = 0;
+  std::vector<PassInfo> passes_;
+  tstring logopath_;
+  int video_ = 0;
+
+  static bool FileExists(const tstring& p) { FILE* f = fopen(p.c_str(), "rb"); if (f) fclose(f); return f != nullptr; }
+
+  void InitEnv() {                                                                       // :389-415
+    env_.reset(new IScriptEnvironment2());
+    BindDevice(env_.get(), device_, consumer_);
+    env_->SetSharedClips(&shared_);
+    AvisynthPluginInit3(env_.get(), nullptr);            // LoadPlugin(Amatsukaze.dll) :414
+    if (envHook_) envHook_(env_.get());
+  }
+
+  // function MakeSource(bool "mt") (:441-475): AMTSource + the logo erasers; Prefetch and Trim belong to AviSynth / the
+  // stream-reform stage and are not reproduced.
+  static AVSValue __cdecl MakeSourceThunk(AVSValue, void* self, IScriptEnvironment* env) { return static_cast<AMTFilterSource*>(self)->MakeSource(env); }
+  AVSValue MakeSource(IScriptEnvironment* env) {
+    AVSValue last = env->Invoke("AMTSource", AVSValue(std::vector<AVSValue>{ AVSValue(setting_.getTmpAMTSourcePath(video_)) }));
+    auto eraseLogo = [&](const tstring& logo, const tstring& logoFramePath, bool forceEnable) {
+      if (!(forceEnable || FileExists(logoFramePath))) return;
+      AVSValue analyze = env->Invoke("AMTAnalyzeLogo", AVSValue(std::vector<AVSValue>{ last, AVSValue(logo), AVSValue() }));
+      last = env->Invoke("AMTEraseLogo", AVSValue(std::vector<AVSValue>{ last, analyze, AVSValue(logo), AVSValue(logoFramePath), AVSValue(),
+                                                                          AVSValue(setting_.getMaxFadeLength()) }));
+    };
+    if (!setting_.isNoDelogo() && logopath_.size() > 0) eraseLogo(logopath_, setting_.getTmpLogoFramePath(video_), true);
+    const auto& el = setting_.getEraseLogoPath();
+    for (int i = 0; i < (int)el.size(); ++i) eraseLogo(el[i], setting_.getTmpLogoFramePath(video_, i), false);
+    return last;
+  }
+
+  // returns: was this pass a pre-process?                                               (:519-544)
+  bool FilterPass(int pass, int gpuIndex, EncodeFileKey key, const tstring& logopath, const FilterScript& mainScript) {
+    InitEnv();
+    logopath_ = logopath; video_ = key.video;
+    env_->AddFunction("MakeSource", "[mt]b", MakeSourceThunk, this);
+    env_->SetVar("AMT_SOURCE", env_->Invoke("MakeSource", AVSValue(true)));
+    env_->SetVar("AMT_TMP", AVSValue(setting_.getAvsTmpPath(key.video)));
+    env_->SetVar("AMT_PASS", AVSValue(pass));
+    env_->SetVar("AMT_DEV", AVSValue(gpuIndex));
+    env_->SetVar("last", env_->GetVar("AMT_SOURCE"));
+    if (mainScript) mainScript(env_.get());
+    return env_->GetVarDef("AMT_PRE_PROC", AVSValue(false)).AsBool();
+  }
+
+  void ReadAllFrames(int pass) {                                                         // :417-439
+    PClip clip = env_->GetVar("last").AsClip();
+    const VideoInfo vi = clip->GetVideoInfo();
+    ctx.infoF("filter pass %d: %d frames", pass + 1, vi.num_frames);
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < vi.num_frames; ++i) PVideoFrame frame = clip->GetFrame(i, env_.get());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    passes_.push_back(PassInfo{ pass, true, vi.num_frames, (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) });
+  }
+
+  void readTimecode(EncodeFileKey key) {                                                 // :189-212
+    const tstring timecodepath = setting_.getAvsTimecodePath(key.video);
+    if (!FileExists(timecodepath)) return;
+    TimecodeFile tc;
+    if (tc.read(timecodepath)) { timeCodes_ = tc.timeCodes; vfrTimingFps_ = tc.vfrTimingFps; }
+  }
+  void MakeOutFormat() { outvi_ = filter_->GetVideoInfo(); }                             // :600-612 (format bookkeeping only)
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// CMAnalyze (CMAnalyze.hpp:22-317) -- the logo-analysis half only: the constructor runs logoFrame() when logos are
+// configured and exposes getLogoPath().  chapter_exe / join_logo_scp subprocesses, Trim/zone parsing (:319-679) are
+// out of scope (SURVEY section 8).  ConfigWrapper is reduced to the accessors logoFrame() reads.
+// ---------------------------------------------------------------------------------------------------------------
+
 
 class CMAnalyze {
 public:
@@ -737,5 +1114,6 @@ extern "C" inline const char* __stdcall AvisynthPluginInit3(IScriptEnvironment* 
   env->AddFunction("AMTEraseLogo", "ccs[logof]s[mode]i[maxfade]i", logo::AMTEraseLogo::Create, 0);
   env->AddFunction("AMTDecimate", "c[duration]s", AMTDecimate::Create, 0);
   env->AddFunction("AMTCombAnalyze", "c[filepath]s", AMTCombAnalyze::Create, 0);
+  env->AddFunction("KFMDeint", "c[mode]i[pass]i[filepath]s[dev]i", CreateKFMDeint, 0);      // pass protocol only (see CreateKFMDeint)
   return "Amatsukaze plugin (B200 hot path)";
 }

@@ -69,6 +69,7 @@ AMTK_API int amtk_device_alloc(amtk_ctx* ctx, size_t bytes, void** out);
 AMTK_API void amtk_device_free(amtk_ctx* ctx, void* p);
 AMTK_API int amtk_memcpy_h2d(amtk_ctx* ctx, void* dst_device, const void* src_host, size_t bytes);
 AMTK_API int amtk_memcpy_d2h(amtk_ctx* ctx, void* dst_host, const void* src_device, size_t bytes);
+AMTK_API int amtk_memcpy_d2d(amtk_ctx* ctx, void* dst_device, const void* src_device, size_t bytes);   /* MakeWritable of a device frame */
 
 /* ---------------------------------------------------------------------------------------------
  * Clip descriptor: a run of planar YUV frames, either resident in HBM or in host memory.
@@ -218,6 +219,11 @@ AMTK_API int amtk_erase_logo_frames(amtk_ctx* ctx, const amtk_clip* clip, const 
                                     int frame0, int nframes, const float* fades);
 /* AMTEraseLogo::CalcFade2 (LogoScan.hpp:1263-1315) on host records (float[num_records][33]). */
 AMTK_API void amtk_calc_fade2(const float* records, int num_records, int num_frames, int n, float* fade_t, float* fade_b);
+/* The same decision without materialising every record of the clip: CalcFade2 reads nine records around frame n
+ * (offsets i = -4..4, with the reference's double offset, :1273-1275).  _index gives the record each offset reads,
+ * _records decides from those nine (float[9][33], offset order). */
+AMTK_API int amtk_calc_fade2_index(int num_records, int num_frames, int n, int i);
+AMTK_API void amtk_calc_fade2_records(const float* rec9, float* fade_t, float* fade_b);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,64 @@ int main(int argc, char** argv) {
       for (int n = 0; n < nframes; ++n) er.GetFades(n, fades[2 * n], fades[2 * n + 1], env);
       FILE* fp = fopen(argv[7], "wb"); fwrite(fades.data(), sizeof(float), fades.size(), fp); fclose(fp);
       printf("fades=%d\n", nframes);
+    } else if (mode == "fieldplan" && argc == 3) {       // picture structures as digits, e.g. 0343663
+      std::vector<uint8_t> pics;
+      for (const char* p = argv[2]; *p; ++p) pics.push_back((uint8_t)(*p - '0'));
+      const std::vector<av::FilterSourceFrame> fr = av::MakeFilterSourceFrames(pics);
+      std::vector<int32_t> top, bottom;
+      av::MakeFieldPlan(fr, top, bottom);
+      printf("frames=%zu:", fr.size());
+      for (size_t k = 0; k < fr.size(); ++k) printf(" %d%s/%d,%d@%.1f", fr[k].decoded, fr[k].halfDelay ? "h" : "", top[k], bottom[k], fr[k].pts);
+      printf("\n");
+    } else if (mode == "filterpass" && argc == 5) {      // tmpdir nframes script(vfr|cfr|none|four|throw)
+      // AMTFilterSource's pass loop on a CPU-only source: which passes run, what the script sees, what gets appended.
+      struct CountingClip : BlankClip {
+        int* pulls;
+        CountingClip(const VideoInfo& vi, int* p) : BlankClip(vi), pulls(p) {}
+        PVideoFrame __stdcall GetFrame(int n, IScriptEnvironment* env) override { ++*pulls; return BlankClip::GetFrame(n, env); }
+      };
+      static int g_pulls = 0, g_opens = 0;
+      static VideoInfo g_vi;
+      g_vi.width = 64; g_vi.height = 32; g_vi.pixel_type = VideoInfo::CS_YV12; g_vi.num_frames = atoi(argv[3]);
+      ConfigWrapper setting; setting.tmpDir = argv[2];
+      const std::string which = argv[4];
+      std::string log;
+      auto hook = [](IScriptEnvironment* env) {           // AMTSource without a device: a counting blank clip
+        env->AddFunction("AMTSource", "s[filter]s[outqp]b", [](AVSValue, void*, IScriptEnvironment*) -> AVSValue {
+          ++g_opens; return AVSValue(PClip(new CountingClip(g_vi, &g_pulls))); }, nullptr);
+      };
+      FilterScript script;
+      if (which == "vfr" || which == "cfr") {
+        // the decision passes need the device; here the pre-process passes just leave the side files behind
+        script = [&](IScriptEnvironment* env) {
+          const int pass = env->GetVar("AMT_PASS").AsInt();
+          const int npre = which == "vfr" ? 2 : 1;
+          log += "pass" + std::to_string(pass) + "(dev=" + std::to_string(env->GetVar("AMT_DEV").AsInt()) + ",tmp=" + env->GetVar("AMT_TMP").AsString() + ") ";
+          env->SetVar("AMT_PRE_PROC", AVSValue(pass < npre));
+          if (pass == npre - 1) {                         // last pre-process: duration (every 5th frame lasts 2) + timecode
+            const std::string base = env->GetVar("AMT_TMP").AsString();
+            FILE* fd = fopen((base + ".duration.txt").c_str(), "w"); FILE* ft = fopen((base + ".timecode.txt").c_str(), "w");
+            int src = 0, nout = 0;
+            while (src < g_vi.num_frames) { const int d = (nout % 4 == 3 && src + 2 <= g_vi.num_frames) ? 2 : 1; fprintf(fd, "%d\n", d); fprintf(ft, "%d\n", (int)(src * 1001.0 / 30 + 0.5)); src += d; ++nout; }
+            fprintf(ft, "# total: %.6f\n", src * 1.001 / 30);
+            fclose(fd); fclose(ft);
+          }
+        };
+      } else if (which == "four") {                       // a script that is ALWAYS a pre-process: 4 passes, then the output build
+        script = [&](IScriptEnvironment* env) { log += "pass" + std::to_string(env->GetVar("AMT_PASS").AsInt()) + " "; env->SetVar("AMT_PRE_PROC", AVSValue(true)); };
+      } else if (which == "throw") {
+        script = [&](IScriptEnvironment* env) { env->ThrowError("script failed in pass %d", env->GetVar("AMT_PASS").AsInt()); };
+      }
+      AMTContext ctx;
+      try {
+        AMTFilterSource fs(ctx, setting, nullptr, 3, EncodeFileKey{ 0 }, "", script, nullptr, DEV_TYPE_CPU, hook);
+        printf("script: %s\n", log.c_str());
+        printf("preproc_passes=%zu opens=%d pulls=%d out_frames=%d timecodes=%zu vfrfps=%d\n", fs.getPasses().size(), g_opens, g_pulls,
+               fs.getVideoInfo().num_frames, fs.getTimeCodes().size(), fs.getVfrTimingFps());
+        printf("is_decimate=%d\n", dynamic_cast<AMTDecimate*>(fs.getClip().get()) != nullptr);
+      } catch (const AviSynthException& e) {
+        printf("AviSynthException: %s\n", e.what());
+      }
     } else {
       fprintf(stderr, "unknown mode / wrong arguments\n");
       return 2;

@@ -182,3 +182,43 @@ def test_eraselogo_fade_selection(exe, tmp_path):
     assert "Start and End must be cyclic" in r.stdout
     r = run(exe, "fades", tmp_path / "none.lgd", "-", rp, n, maxfade, fp, ok=(4,))
     assert "Failed to read logo file" in r.stdout
+
+
+def test_filter_source_pass_loop(exe, tmp_path):
+    """AMTFilterSource (FilteredSource.hpp:232-275,519-544): fresh environment per pass, AMT_* variables, AMT_PRE_PROC decides
+    whether the pass is pulled and discarded, AMTDecimate appended when a duration file was left behind, timecodes read,
+    AvisynthError converted to AviSynthException.  CPU-only source injected through the environment hook."""
+    def run(script, n=23):
+        d = tmp_path / script
+        d.mkdir()
+        r = subprocess.run([exe, "filterpass", str(d), str(n), script], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout
+    s = run("vfr")                      # Misc.cs:1305-1306: pre-process while AMT_PASS < 2
+    assert "script: pass0(dev=3,tmp=" in s and "pass1(dev=3" in s and "pass2(dev=3" in s and "pass3" not in s
+    assert "v0-0-0.avstmp" in s                                    # TranscodeSetting.hpp:875-880
+    assert "preproc_passes=2" in s and "pulls=46" in s             # two passes x 23 frames pulled and discarded
+    assert "out_frames=19" in s and "is_decimate=1" in s           # 23 source frames, four 2-frame durations -> 19
+    assert "timecodes=20" in s and "vfrfps=60" in s                # 19 stamps + "# total:"; 60000/1001 grid fits best
+    s = run("cfr")                      # Misc.cs:1311-1312: one pre-process pass
+    assert "preproc_passes=1" in s and "pulls=23" in s and "pass2" not in s and "is_decimate=1" in s
+    s = run("none")                     # no script: the source is the output, nothing is pulled
+    assert "preproc_passes=0" in s and "pulls=0" in s and "out_frames=23" in s and "is_decimate=0" in s
+    s = run("four")                     # at most four passes (FilteredSource.hpp:232)
+    assert "script: pass0 pass1 pass2 pass3 \n" in s and "preproc_passes=4" in s and "pulls=92" in s
+    s = run("throw")
+    assert "AviSynthException: script failed in pass 0" in s      # :289-295
+
+
+def test_source_frame_list_and_field_plan(exe):
+    """StreamReform.hpp:874-904 (picture structure -> source frames) and AMTSource.hpp:524-551 (half-delay frames take their
+    top field from the previous decoded picture; a repeated picture yields a second, undelayed frame)."""
+    def run(pics):
+        r = subprocess.run([exe, "fieldplan", pics], capture_output=True, text=True, timeout=30)
+        assert r.returncode == 0
+        return r.stdout.strip()
+    # 0 FRAME, 3 TFF, 4 BFF, 6 BFF_RFF, 1 DOUBLING, 2 TRIPLING, 5 TFF_RFF
+    assert run("0343663") == ("frames=9: 0/0,0@0.0 1/1,1@1.0 2h/1,2@1.5 3/3,3@3.0 4h/3,4@3.5 4/4,4@4.5 5h/4,5@5.5 5/5,5@6.5 6/6,6@8.0")
+    assert run("125") == "frames=6: 0/0,0@0.0 0/0,0@1.0 1/1,1@2.0 1/1,1@3.0 1/1,1@4.0 2/2,2@5.0"
+    # a delayed first picture has no predecessor: no frame is made for it and GetFrame serves the next cached one (:567-577)
+    assert run("4412").startswith("frames=7: 0h/0,1@-0.5 1h/0,1@0.5 2/2,2@2.0 2/2,2@3.0")
