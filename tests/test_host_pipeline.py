@@ -69,7 +69,8 @@ def test_filter_source_with_logo_eraser_in_make_source(exe, tmp_path):
     _write_raw1(tmp_path / "amts0.dat", frames)
     logo_path = str(tmp_path / "logo.lgd")
     ab.Logo.create(lg["data"], 64, 64, W, H, IMGX, IMGY).save(logo_path)
-    open(tmp_path / "logof0.txt", "w").write("")            # empty logoframe file: CalcFade2 decides every frame
+    # logoframe file (LogoScan.hpp:1818-1819 format): logo fading in around frame 6, out around frame 30
+    open(tmp_path / "logof0.txt", "w").write("%6d S 0 ALL %6d %6d\n%6d E 0 ALL %6d %6d\n" % (6, 5, 7, 30, 28, 32))
     r = subprocess.run([exe, "passes", str(tmp_path), logo_path, "cfr"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "passes: preproc=1 uploads=1 out_frames=40" in r.stdout
@@ -78,9 +79,15 @@ def test_filter_source_with_logo_eraser_in_make_source(exe, tmp_path):
     de, top, bot = raw.deint().create_mask(0.35), raw.field(0).create_mask(0.35), raw.field(1).create_mask(0.35)
     Y, _, _ = synth.split_planes(frames, W, H)
     rec = np.stack([po.or_analyze_frame(de, top, bot, Y[i]) for i in range(n)])
+    fr = np.zeros(n, int)                                    # ReadLogoFrameFile (:1421-1461)
+    fr[5:8] = 1; fr[7:29] = 2; fr[29:33] = 1
     changed = 0
     for k, i in enumerate(range(0, n, 5)):
-        ft, fb = po.or_calc_fade2(rec, n, i)
+        win = [fr[max(0, min(n - 1, i + d))] for d in range(-8, 9)]          # CalcFade (:1317-1341), maxfade 16
+        if all(v == win[0] for v in win):
+            ft = fb = 1.0 if fr[i] == 2 else 0.0
+        else:
+            ft, fb = po.or_calc_fade2(rec, n, i)
         Yi, Ui, Vi = [np.ascontiguousarray(p[i]) for p in synth.split_planes(frames.copy(), W, H)]
         po.or_erase_frame(raw, Yi, Ui, Vi, ft, fb)
         exp = np.concatenate([Yi.ravel(), Ui.ravel(), Vi.ravel()])
@@ -121,7 +128,7 @@ def test_amtsource_ingest_semantics(exe, tmp_path, nv12):
         elif p == 4: plan.append((d - 1, d))
         elif p == 6: plan += [(d - 1, d), (d, d)]
     out = np.fromfile(tmp_path / "out.bin", np.uint8).reshape(-1, w * h * 3 // 2)
-    assert out.shape[0] == len(plan) == 17
+    assert out.shape[0] == len(plan) == 16
     for k, (t, b) in enumerate(plan):
         exp = dec[b].copy()
         for (off, ph, pw) in ((0, h, w), (ysz, h // 2, w // 2), (ysz + csz, h // 2, w // 2)):
