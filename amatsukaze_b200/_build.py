@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
     obj = os.path.join(LIBDIR, "logo_host.o")
     cmd1 = ["g++", "-std=c++17", *HOST_FLAGS, "-c", os.path.join(CSRC, "logo_host.cpp"), "-o", obj]
     cmd2 = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-shared", "-o", LIB,
-            os.path.join(CSRC, "amtk_b200.cu"), obj]
+            os.path.join(CSRC, "amtk_b200.cu"), obj, "-ldl", "-lpthread"]
     for cmd in (cmd1, cmd2):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:

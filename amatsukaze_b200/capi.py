@@ -89,6 +89,19 @@ SIGNATURES = [
     ("amtk_erase_logo_frames", C.c_int, [V, C.POINTER(ClipDesc), V, C.c_int, C.c_int, c_float_p]),
     ("amtk_calc_fade2", None, [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]),
     ("amtk_calc_fade2_index", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("amtk_group_create", C.c_int, [C.c_int, c_i32_p, VP]),
+    ("amtk_group_destroy", None, [V]),
+    ("amtk_group_size", C.c_int, [V]),
+    ("amtk_group_ctx", V, [V, C.c_int]),
+    ("amtk_group_numa_cpus", C.c_int, [V, C.c_int]),
+    ("amtk_group_nccl_version", C.c_int, [V]),
+    ("amtk_group_host_alloc", C.c_int, [V, C.c_int, C.c_size_t, VP]),
+    ("amtk_group_scan_comb_streams", C.c_int, [V, C.POINTER(ClipDesc), VP, C.POINTER(CombParams), C.c_int]),
+    ("amtk_group_fetch_results", C.c_int, [V, C.c_int, C.c_int, V, V]),
+    ("amtk_group_synchronize", C.c_int, [V]),
+    ("amtk_group_mark", C.c_int, [V, C.c_int]),
+    ("amtk_group_elapsed_ms", C.c_int, [V, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    ("amtk_group_scan_add_frames", C.c_int, [V, VP, C.POINTER(ClipDesc), C.c_int, C.c_int, c_i32_p, c_i32_p]),
     ("amtk_calc_fade2_records", None, [c_float_p, c_float_p, c_float_p]),
 ]
 
@@ -161,9 +174,9 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and not getattr(self, "borrowed", False):
             self.L.amtk_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -280,6 +293,80 @@ class Context:
         out = C.c_void_p()
         check(self.L.amtk_scan_create(self.h, scanw, scanh, log_uvx, log_uvy, thy, C.byref(out)))
         return LogoScanAcc(self, out, scanw, scanh, log_uvx, log_uvy)
+
+
+class Group:
+    """amtk_group: one process driving several devices (context + stream + host thread per device, NCCL for the final
+    gather).  Python is plumbing only; bench.py --gpus N without torchrun goes through this."""
+
+    def __init__(self, ndev, devices=None):
+        self.L = lib()
+        h = C.c_void_p()
+        arr = None
+        if devices is not None:
+            arr = np.ascontiguousarray(devices, np.int32).ctypes.data_as(c_i32_p)
+        check(self.L.amtk_group_create(int(ndev), arr, C.byref(h)))
+        self.h = h
+        self.n = self.L.amtk_group_size(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.amtk_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ctx(self, i):
+        """Borrowed Context of member i (owned by the group: do not close it)."""
+        c = Context.__new__(Context)
+        c.L, c.h, c.device, c.borrowed = self.L, C.c_void_p(self.L.amtk_group_ctx(self.h, i)), i, True
+        return c
+
+    def numa_cpus(self, i):
+        return int(self.L.amtk_group_numa_cpus(self.h, i))
+
+    @property
+    def nccl_version(self):
+        return int(self.L.amtk_group_nccl_version(self.h))
+
+    def host_alloc(self, i, nbytes):
+        """Pinned, NUMA-local host buffer as a numpy uint8 array (freed with the process)."""
+        p = C.c_void_p()
+        check(self.L.amtk_group_host_alloc(self.h, i, nbytes, C.byref(p)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def scan_comb_streams(self, clips, logos, params, nframes):
+        carr = (ClipDesc * self.n)(*clips)
+        larr = (C.c_void_p * self.n)(*[lg.h for lg in logos])
+        check(self.L.amtk_group_scan_comb_streams(self.h, carr, larr, C.byref(params), nframes))
+
+    def fetch_results(self, nframes, src=0):
+        scores = np.empty((self.n, nframes, 2), np.float32)
+        counts = np.empty((self.n, nframes, 12), np.int32)
+        check(self.L.amtk_group_fetch_results(self.h, src, nframes, _ptr(scores), _ptr(counts)))
+        return scores, counts
+
+    def synchronize(self):
+        check(self.L.amtk_group_synchronize(self.h))
+
+    def mark(self, slot):
+        check(self.L.amtk_group_mark(self.h, slot))
+
+    def elapsed_ms(self, a, b):
+        out = (C.c_double * self.n)()
+        check(self.L.amtk_group_elapsed_ms(self.h, a, b, out))
+        return list(out)
+
+    def scan_add_frames(self, scans, clips, scanx, scany, frame0, nframes):
+        sarr = (C.c_void_p * self.n)(*[s.h for s in scans])
+        carr = (ClipDesc * self.n)(*clips)
+        f0 = np.ascontiguousarray(frame0, np.int32)
+        nf = np.ascontiguousarray(nframes, np.int32)
+        check(self.L.amtk_group_scan_add_frames(self.h, sarr, carr, scanx, scany, f0.ctypes.data_as(c_i32_p), nf.ctypes.data_as(c_i32_p)))
 
 
 class Logo:

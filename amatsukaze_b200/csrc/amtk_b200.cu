@@ -1385,3 +1385,5 @@ int amtk_calc_fade2_index(int num_records, int num_frames, int n, int i) { retur
 void amtk_calc_fade2_records(const float* rec9, float* ft, float* fb) { amtk::calc_fade2_records(rec9, ft, fb); }
 
 }  // extern "C"
+
+#include "group.cuh"

@@ -225,6 +225,42 @@ AMTK_API void amtk_calc_fade2(const float* records, int num_records, int num_fra
 AMTK_API int amtk_calc_fade2_index(int num_records, int num_frames, int n, int i);
 AMTK_API void amtk_calc_fade2_records(const float* rec9, float* fade_t, float* fade_b);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: ONE process drives several devices -- a context, a stream and a host thread per device
+ * (each thread pinned to the CPUs next to its GPU), NCCL over NVLink only for the final gather of the small per-frame
+ * result blocks and for the exact integer all-reduce of a frame-sharded LogoScan.  This is what the reference's
+ * job-per-GPU scheduler (AmatsukazeServer/Server/ResourceManager.cs:81-85, Amatsukaze/InterProcessComm.hpp:87-95) would
+ * drive from C++/C#.  NCCL is loaded with dlopen on first use; one device needs no NCCL at all.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct amtk_group amtk_group;
+/* devices: CUDA ordinals (NULL = 0..ndev-1) */
+AMTK_API int amtk_group_create(int ndev, const int* devices, amtk_group** out);
+AMTK_API void amtk_group_destroy(amtk_group* g);
+AMTK_API int amtk_group_size(const amtk_group* g);
+/* the context of member i: create logos / scans / device buffers for that device through it */
+AMTK_API amtk_ctx* amtk_group_ctx(amtk_group* g, int i);
+/* CPUs member i's host thread was bound to (0 = not bound), NCCL version in use (0 = none) */
+AMTK_API int amtk_group_numa_cpus(const amtk_group* g, int i);
+AMTK_API int amtk_group_nccl_version(const amtk_group* g);
+/* pinned host memory allocated and first-touched by member i's thread (NUMA-local to its GPU) */
+AMTK_API int amtk_group_host_alloc(amtk_group* g, int i, size_t bytes, void** out);
+/* BASELINE configs[4]: clips[i] (host or device resident, all with >= nframes frames) is analysed on member i with logos[i]
+ * (amtk_scan_comb_frames semantics, frames [0, nframes)), then ONE ncclAllGather of the per-member result blocks.
+ * Device clips: returns when the work is enqueued (asynchronous); host clips: returns when the staging is done. */
+AMTK_API int amtk_group_scan_comb_streams(amtk_group* g, const amtk_clip* clips, amtk_logo* const* logos,
+                                          const amtk_comb_params* params, int nframes);
+/* gathered results of the last pass as held by member `from`: scores float[ndev][nframes][2], counts int32[ndev][nframes][12] */
+AMTK_API int amtk_group_fetch_results(amtk_group* g, int from, int nframes, float* scores, int32_t* counts);
+AMTK_API int amtk_group_synchronize(amtk_group* g);
+/* device-side timing: mark = one CUDA event per member after everything enqueued so far (compute and collective);
+ * elapsed = milliseconds between two marks per member (take the maximum) */
+AMTK_API int amtk_group_mark(amtk_group* g, int slot);
+AMTK_API int amtk_group_elapsed_ms(amtk_group* g, int slot_a, int slot_b, double* ms_per_member);
+/* frame-sharded LogoScan: member i adds frames [frame0[i], frame0[i]+nframes[i]) of clips[i] to scans[i] (created on
+ * amtk_group_ctx(g, i)), then ONE ncclAllReduce(ncclSum, ncclUint64) leaves the whole-clip sums in every scans[i]. */
+AMTK_API int amtk_group_scan_add_frames(amtk_group* g, amtk_scan* const* scans, const amtk_clip* clips, int scanx, int scany,
+                                        const int* frame0, const int* nframes);
+
 #ifdef __cplusplus
 }
 #endif
