@@ -53,6 +53,8 @@ struct amtk_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;       // H2D staging for host-resident clips
+  cudaStream_t side_stream = nullptr;       // the logo evaluation that runs UNDER the streaming comb kernel (fused step)
+  cudaEvent_t ev_side = nullptr, ev_side_done = nullptr;
   cudaEvent_t ev_copy[2] = { nullptr, nullptr };
   cudaEvent_t ev_done[2] = { nullptr, nullptr };
   int sm_count = 0;
@@ -73,6 +75,9 @@ struct amtk_ctx {
     int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_sync = 0, comb_l2 = 64;
     int comb_item = 0;        // frames per long work item of the warp-stream kernel (0 = auto)
     int comb_ws_stages = 2;  // ring slots per warp stream
+    int lite_ctas = 5;      // CTAs per SM of the small-footprint logo kernel when it runs on its own
+    int scan_lite = 0;      // fused step: 0 = logo_scores after the comb kernel (default); 1 = logo_lite UNDER the comb kernel on the side
+                            // stream (step 1.324 vs 1.339 ms, but the comb kernel itself stretches 1.225 -> 1.309 ms); 2 = logo_lite alone (1.370 ms)
     int comb_ws = 1;        // 1: round-2 warp-stream kernel for 8-bit clips (comb_stream.cuh); 0: round-1 CTA-ring kernel
   } knobs;
   // cached launch plan of the streaming comb kernel: work items on the device + occupancy, keyed by geometry and range

@@ -203,6 +203,71 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __gr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// logo_lite_kernel: the same per-pixel scores as logo_scores_kernel, built to CO-RESIDE with the streaming comb kernel.
+// The fused step (amtk_scan_comb_frames) used to run comb (1.22 ms) and then logo_scores (0.10 ms) back to back: the logo
+// work is ~1.5 % of the comb kernel's instructions but, as a kernel of its own, it is latency bound (one 512-thread CTA
+// per SM, three block barriers per frame) and owns the whole chip while it runs.  This variant needs 128 threads,
+// <= 104 registers and <= 29 KB of shared memory -- exactly what three resident comb CTAs leave free on an SM -- so it
+// runs on a side stream UNDER the comb kernel and its latencies fill issue slots the comb warps leave empty.
+// Differences from logo_scores_kernel: the 25 taps of a feature pixel are read from L2 (tap-major table, coalesced)
+// instead of living in registers; A/B come from L2; the deinterlaced source is recomputed from the raw ROI per fade.
+// The arithmetic (expression trees, rounding) is the same code from exact_math.h.  ScanFrame semantics only
+// (DeintY source, ROI = the logo rectangle).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kLiteThreads = 128;
+struct LiteJob {
+  const void* ybase; long long frame_stride; int pitch;      // Y plane of the window, pitch in ELEMENTS
+  int frame0, nframes;
+  int imgx, imgy;
+  LogoDev logo;
+  float maxv;
+  int nfades; float fades[4];
+  float* scores;                                             // [nframes][nfades][countPad]
+};
+__host__ __device__ inline size_t logo_lite_smem_bytes(int w, int h, int bps) {
+  return (((size_t)w * h + 8 + 3) & ~(size_t)3) * sizeof(float) + (((size_t)w * h * bps + 15) & ~(size_t)15) + 16;
+}
+
+template <typename pixel_t>
+__global__ void __launch_bounds__(kLiteThreads, 4) logo_lite_kernel(const LiteJob job) {
+  extern __shared__ __align__(16) float lite_smem[];
+  const LogoDev& lg = job.logo;
+  const int w = lg.w, h = lg.h, npx = w * h, tid = threadIdx.x;
+  float* work = lite_smem;
+  pixel_t* raw = reinterpret_cast<pixel_t*>(lite_smem + ((npx + 8 + 3) & ~3));
+  for (int f = blockIdx.x; f < job.nframes; f += gridDim.x) {
+    const pixel_t* roi = reinterpret_cast<const pixel_t*>(reinterpret_cast<const uint8_t*>(job.ybase) + (long long)(job.frame0 + f) * job.frame_stride) +
+                         job.imgx + (long long)job.imgy * job.pitch;
+    for (int i = tid; i < npx; i += kLiteThreads) { const int y = i / w, x = i - y * w; raw[i] = roi[x + (long long)y * job.pitch]; }
+    __syncthreads();
+    for (int fi = 0; fi < job.nfades; ++fi) {
+      const float fade = job.fades[fi], omf = AMTK_FSUB(1.0f, fade);
+      for (int i = tid; i < npx; i += kLiteThreads) {
+        const int y = i / w;
+        float v;                                             // DeintY (:763-780)
+        if (y > 0 && y < h - 1) { const int a = raw[i - w], b = raw[i], c = raw[i + w]; v = (float)(a + 2 * b + c + 2) / 4.0f; }
+        else v = (float)raw[i];
+        work[i] = remove_logo(v, __ldg(lg.A + i), __ldg(lg.B + i), job.maxv, fade, omf);
+      }
+      __syncthreads();
+      float* out = job.scores + ((size_t)f * job.nfades + fi) * lg.countPad;
+      for (int c = tid; c < lg.count; c += kLiteThreads) {
+        const uint32_t pv = __ldg(lg.pix + c);
+        const float* wp = work + (int)((pv & 0xFFFFu) - 2) + (int)((pv >> 16) - 2) * w;
+        float taps[25];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) taps[t] = __ldg(lg.tapsT + (size_t)t * lg.countPad + c);
+        float avg;
+        const float sum = corr5x5_tree(taps, [&](int dy, int dx) { return wp[dy * w + dx]; }, &avg);
+        const float2 sc = __ldg(lg.scales + (size_t)c * 32 + scale_bin(avg));
+        out[c] = pixel_score(sum, sc.x, sc.y);
+      }
+      __syncthreads();                                       // `work` is rewritten by the next fade / `raw` by the next frame
+    }
+  }
+}
+
 // One thread per (frame, fade): ordered float sum of the pixel scores, divided by blackScore (:252-254,310).
 // out index = frame*out_frame_stride + out_off + fade*out_fade_stride; take_abs for AMTAnalyzeLogo (:1152-1154).
 // The chain of ~1.3k dependent FADDs is inherent (the order is the reference's); the loads are software-pipelined

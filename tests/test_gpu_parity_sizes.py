@@ -243,3 +243,39 @@ def test_one_context_from_two_threads(ctx, oracle):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errors, errors[:5]
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_fused_step_with_coresident_logo_kernel(oracle, monkeypatch, mode):
+    """AMTK_SCAN_LITE=1: the logo evaluation of the fused step runs on a side stream UNDER the comb kernel (small-footprint
+    kernel, taps from L2); =2: the same kernel on its own.  Not the default but kept tested: identical
+    bits, 8- and 10-bit, device and host clips."""
+    po = oracle
+    w, h, n, imgx, imgy = 640, 360, 50, 500, 40
+    lg = synth.make_logo(64, 64)
+    monkeypatch.setenv("AMTK_SCAN_LITE", mode)
+    c = ab.Context(0, torch.cuda.current_stream().cuda_stream)
+    monkeypatch.delenv("AMTK_SCAN_LITE")
+    try:
+        f8 = _gen(7, n, w, h, logo=lg, imgx=imgx, imgy=imgy, logo_period=20)
+        logo = ab.Logo.create(lg["data"], 64, 64, w, h, imgx, imgy).deint().create_mask(0.35)
+        o = po.OracleLogo.create(lg["data"], 64, 64, w, h, imgx, imgy).deint().create_mask(0.35)
+        prm = ab.default_comb_params()
+        for rep in range(2):
+            s, cn = c.scan_comb_frames(ab.yv12_clip(f8, w, h, n, True), [logo], prm)
+        Y, U, V = synth.split_planes(f8, w, h)
+        rs = np.stack([o.scan_frame(Y[i]) for i in range(n)])
+        rc = po.or_comb_clip(Y, U, V, prm.as_list())
+        assert np.array_equal(_bits(s.cpu().numpy()[:, 0]), _bits(rs)) and np.array_equal(cn.cpu().numpy(), rc)
+        s2, c2 = c.scan_comb_frames(ab.yv12_clip(f8.cpu().numpy(), w, h, n, False), [logo], prm)
+        assert np.array_equal(_bits(s2[:, 0]), _bits(rs)) and np.array_equal(c2, rc)
+        f16 = (f8.to(torch.int32) * 4 + (f8.to(torch.int32) & 3)).to(torch.int16).contiguous()
+        p10 = ab.default_comb_params()
+        p10.th_move_y, p10.th_shima_y, p10.th_lshima_y = 80, 48, 144
+        s10, c10 = c.scan_comb_frames(ab.yv12_clip(f16, w, h, n, True, bits=10), [logo], p10)
+        a16 = f16.cpu().numpy().view(np.uint16)
+        Y10 = a16[:, :w * h].reshape(n, h, w)
+        rs10 = np.stack([o.scan_frame(Y10[i], maxv=1023.0) for i in range(n)])
+        assert np.array_equal(_bits(s10.cpu().numpy()[:, 0]), _bits(rs10))
+    finally:
+        c.close()
