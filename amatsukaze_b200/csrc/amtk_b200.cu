@@ -5,6 +5,7 @@
 #include "logo_kernels.cuh"
 #include "comb_kernels.cuh"
 #include "comb_stream.cuh"
+#include "comb_mma.cuh"
 #include "scan_kernels.cuh"
 #include <algorithm>
 #include <cfloat>
@@ -362,10 +363,11 @@ static int pick_comb_R(int hY, int hC) {
 }
 
 // ---- round-2 streaming kernel (comb_stream.cuh): independent warp streams, 8-bit samples ----------------------
-struct WsVariant { int R, stages, TH, boxH, smem; void (*kernel)(const WsArgs); };
-template <typename Cfg> static WsVariant make_ws() { return WsVariant{ Cfg::R, Cfg::STAGES, Cfg::TH, Cfg::BOXH, Cfg::SMEM, comb_ws_kernel<Cfg> }; }
+struct WsVariant { int R, stages, warps, TH, boxH, smem; void (*kernel)(const WsArgs); };
+template <typename Cfg> static WsVariant make_ws() { return WsVariant{ Cfg::R, Cfg::STAGES, Cfg::WARPS, Cfg::TH, Cfg::BOXH, Cfg::SMEM, comb_ws_kernel<Cfg> }; }
 static const WsVariant* ws_variants(int* n) {
-  static const WsVariant v[] = { make_ws<WsCfg<17, 2>>(), make_ws<WsCfg<15, 2>>(), make_ws<WsCfg<16, 2>>(), make_ws<WsCfg<9, 2>>(), make_ws<WsCfg<15, 3>>(), make_ws<WsCfg<12, 2>>(), make_ws<WsCfg<10, 2>>() };
+  static const WsVariant v[] = { make_ws<WsCfg<17, 2>>(), make_ws<WsCfg<15, 2>>(), make_ws<WsCfg<16, 2>>(), make_ws<WsCfg<9, 2>>(), make_ws<WsCfg<15, 3>>(), make_ws<WsCfg<12, 2>>(), make_ws<WsCfg<10, 2>>(),
+                                 make_ws<WsCfg<15, 2, 7>>(), make_ws<WsCfg<13, 2, 5>>(), make_ws<WsCfg<15, 2, 2>>(), make_ws<WsCfg<15, 3, 3>>() };
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }
@@ -386,8 +388,9 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   const int wY = clip->width, wC = clip->width >> clip->log_uvx;
   const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_ws_R(hY, hC);
   int nvar = 0; const WsVariant* vars = ws_variants(&nvar); const WsVariant* V = nullptr;
-  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].stages == ctx->knobs.comb_ws_stages) V = &vars[i];
+  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].stages == ctx->knobs.comb_ws_stages && vars[i].warps == ctx->knobs.comb_ws_warps) V = &vars[i];
   if (!V) AMTK_FAIL("comb: no warp-stream kernel variant for the requested AMTK_COMB_* settings");
+  const int WW = V->warps;
   WsArgs args;
   memset(&args, 0, sizeof(args));
   const CUtensorMapL2promotion promo = ctx->knobs.comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : ctx->knobs.comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
@@ -443,7 +446,7 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   if (plan.occ_kernel != (const void*)V->kernel) {          // once per kernel variant, not per launch
     int occ = 0;
     AMTK_CUDA(cudaFuncSetAttribute(V->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V->smem));
-    AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, V->kernel, 32 * kWsWarps, V->smem));
+    AMTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, V->kernel, 32 * WW, V->smem));
     if (occ < 1) AMTK_FAIL("comb kernel does not fit on an SM");
     plan.occ = occ; plan.occ_kernel = (const void*)V->kernel; plan.valid = false;
   }
@@ -454,11 +457,11 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   // that all warps run dry within about one short item of each other.  The item list depends only on the geometry and
   // the frame range, so it stays on the device between calls (a 1-frame GetFrame call re-uses it without any copy).
   const long long total = (long long)ntiles * nf;
-  const int nwarps = ctx->sm_count * occ * kWsWarps;
-  const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (total + kWsWarps - 1) / kWsWarps);
+  const int nwarps = ctx->sm_count * occ * WW;
+  const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (total + WW - 1) / WW);
   const int f0 = lo - win.first;
   if (!(plan.valid && plan.wY == wY && plan.hY == hY && plan.wC == wC && plan.hC == hC && plan.nf == nf && plan.f0 == f0 &&
-        plan.R == V->R && plan.item == ctx->knobs.comb_item && plan.ctas == occ)) {
+        plan.R == V->R && plan.item == ctx->knobs.comb_item && plan.ctas == occ * WW)) {
     int big = ctx->knobs.comb_item > 0 ? ctx->knobs.comb_item : 64, small = std::max(4, big / 4);
     // each warp should see at least ~6 big items; shrink for short clips
     while (big > 8 && (long long)ntiles * (nf / big) < 6LL * nwarps) { big /= 2; small = std::max(4, big / 4); }
@@ -478,6 +481,111 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
     AMTK_CUDA(cudaStreamSynchronize(ctx->stream));           // pageable source vector dies at the end of this scope
     plan.nitems = (int)segs.size();
     plan.wY = wY; plan.hY = hY; plan.wC = wC; plan.hC = hC; plan.nf = nf; plan.f0 = f0; plan.R = V->R;
+    plan.item = ctx->knobs.comb_item; plan.ctas = occ * WW; plan.valid = true;
+  }
+  AMTK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(plan.dev) + plan.q_off, 0, 256, ctx->stream));
+  args.segs = reinterpret_cast<const CombSegment*>(plan.dev);
+  args.nitems = plan.nitems;
+  args.queue = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(plan.dev) + plan.q_off);
+  args.counts = dcounts;
+  args.out_frame0 = out_row0 - win.first;
+  AMTK_CUDA(cudaMemsetAsync(dcounts + (size_t)(lo - out_row0) * 12, 0, (size_t)nf * 12 * sizeof(int), ctx->stream));
+  std::pair<cudaEvent_t, cudaEvent_t> ev{ nullptr, nullptr };
+  if (ctx->timing) {
+    if (!ctx->timing_pool.empty()) { ev = ctx->timing_pool.back(); ctx->timing_pool.pop_back(); }
+    else { AMTK_CUDA(cudaEventCreate(&ev.first)); AMTK_CUDA(cudaEventCreate(&ev.second)); }
+    AMTK_CUDA(cudaEventRecord(ev.first, ctx->stream));
+  }
+  args.prefetch = ctx->knobs.comb_ws_prefetch;
+  V->kernel<<<grid, 32 * WW, V->smem, ctx->stream>>>(args);
+  AMTK_CUDA(cudaGetLastError());
+  if (ctx->timing) { AMTK_CUDA(cudaEventRecord(ev.second, ctx->stream)); ctx->timing_events.push_back(ev); }
+  ctx->launches += 1;
+  return 1;
+}
+
+// ---- tensor-core streaming kernel (comb_mma.cuh): one CTA = one tile stream, stencil as two tcgen05.mma per tile-frame ----
+static int launch_comb_mma(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi,
+                           const amtk_comb_params* prm, int* dcounts, int out_row0) {
+  const int hY = clip->height, hC = clip->height >> clip->log_uvy;
+  const int wY = clip->width, wC = clip->width >> clip->log_uvx;
+  WsArgs args;
+  memset(&args, 0, sizeof(args));
+  const CUtensorMapL2promotion promo = ctx->knobs.comb_l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : ctx->knobs.comb_l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                                       ctx->knobs.comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  for (int pl = 0; pl < 3; ++pl) {
+    const long long off = pl == 0 ? 0 : (pl == 1 ? clip->off_u : clip->off_v);
+    cuuint64_t gdim[3] = { (cuuint64_t)(pl ? wC : wY), (cuuint64_t)(pl ? hC : hY), (cuuint64_t)win.count };
+    cuuint64_t gstr[2] = { (cuuint64_t)(pl ? clip->pitch_uv : clip->pitch_y), (cuuint64_t)clip->frame_stride };
+    cuuint32_t box[3] = { (cuuint32_t)kMmTW, (cuuint32_t)kMmBoxH, 1u };
+    cuuint32_t estr[3] = { 1u, 1u, 1u };
+    // 128-byte swizzle: the staged tile is the MN-major A operand of the MMA as it lands
+    if (ctx->encode_tiled(&args.map[pl], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(win.dev_base) + off, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      AMTK_FAIL("cuTensorMapEncodeTiled failed");
+  }
+  const int tyY = (hY + kMmTH - 1) / kMmTH, tyC = (hC + kMmTH - 1) / kMmTH;
+  int tile0 = 0, nc = 0;
+  for (int pl = 0; pl < 3; ++pl) {
+    WsClass& C = args.cl[nc];
+    const bool chroma = pl != 0;
+    C.kind = 0; C.map = pl; C.cls = chroma ? 1 : 0; C.H = chroma ? hC : hY;
+    C.thM = (unsigned)(0x80 - (chroma ? prm->th_move_c : prm->th_move_y)) * 0x01010101u;
+    C.thS = (unsigned)(chroma ? prm->th_shima_c : prm->th_shima_y) * 0x00010001u;
+    C.thL = (unsigned)(chroma ? prm->th_lshima_c : prm->th_lshima_y) * 0x00010001u;
+    C.tilesX = ((chroma ? wC : wY) + kMmTW - 1) / kMmTW;
+    C.tile0 = tile0; C.ntiles = C.tilesX * (chroma ? tyC : tyY);
+    if (C.ntiles == 0) continue;
+    tile0 += C.ntiles; ++nc;
+  }
+  args.nclasses = nc;
+  const int ntiles = tile0, nf = hi - lo;
+  amtk_ctx::CombPlan& plan = ctx->plan;
+  // NS tiles per CTA step (AMTK_COMB_MMA = 1 or 2).  Dynamic shared memory is padded so that exactly 4 / NS CTAs share an
+  // SM: their 128 * NS tensor-memory columns each add up to all 512.
+  const int NS = ctx->knobs.comb_mma == 2 ? 2 : 1;
+  void (*kern)(const WsArgs) = NS == 2 ? comb_mma_kernel<2> : comb_mma_kernel<1>;
+  const int smem = NS == 2 ? 110 * 1024 : 55 * 1024;
+  static_assert(2 * kMmSmemPerStream + kMmBandBytes + 1024 <= 110 * 1024 && kMmSmemPerStream + kMmBandBytes + 1024 <= 55 * 1024, "comb_mma: shared-memory budget");
+  if (plan.occ_kernel != (const void*)kern) {
+    AMTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // Residency is set by construction, not queried (the occupancy API answers 1 for a kernel that allocates tensor memory)
+    plan.occ = 4 / NS; plan.occ_kernel = (const void*)kern; plan.valid = false;
+  }
+  int occ = plan.occ;
+  if (ctx->knobs.comb_ctas > 0) occ = std::min(occ, ctx->knobs.comb_ctas);
+  const int npairs_t = (ntiles + NS - 1) / NS;               // a CTA streams NS tiles at a time
+  const long long total = (long long)npairs_t * nf;
+  const int nstreams = ctx->sm_count * occ;
+  const int grid = (int)std::min<long long>(nstreams, total);
+  const int f0 = lo - win.first;
+  if (!(plan.valid && plan.wY == wY && plan.hY == hY && plan.wC == wC && plan.hC == hC && plan.nf == nf && plan.f0 == f0 &&
+        plan.R == 1000 * NS + kMmTH && plan.item == ctx->knobs.comb_item && plan.ctas == occ)) {
+    int big = ctx->knobs.comb_item > 0 ? ctx->knobs.comb_item : 64, small = std::max(4, big / 4);
+    while (big > 8 && (long long)npairs_t * (nf / big) < 6LL * nstreams) { big /= 2; small = std::max(4, big / 4); }
+    const int tail_frames = std::min(nf, std::max(small, (int)(nf * 0.15)));
+    const int head_frames = nf - tail_frames;
+    // Items come in PAIRS (2i, 2i+1) with the same frame range; an odd tile count is padded with a filler (tile = ~t: the
+    // last tile once more, results dropped).  Frame-block-major order: CTAs running at the same time work on the same
+    // frames of neighbouring tiles, so halo rows and straddled lines are shared through L2.
+    std::vector<CombSegment> segs;
+    segs.reserve((size_t)NS * npairs_t * (head_frames / big + tail_frames / small + 2));
+    auto push_block = [&](int fa, int fz) {
+      for (int t = 0; t < ntiles; t += NS) {
+        segs.push_back(CombSegment{ t, fa, fz });
+        if (NS == 2) segs.push_back(CombSegment{ t + 1 < ntiles ? t + 1 : ~t, fa, fz });
+      }
+    };
+    for (int f = 0; f < head_frames; f += big) push_block(f0 + f, f0 + std::min(head_frames, f + big));
+    for (int f = head_frames; f < nf; f += small) push_block(f0 + f, f0 + std::min(nf, f + small));
+    const size_t seg_bytes = segs.size() * sizeof(CombSegment);
+    plan.q_off = (seg_bytes + 255) & ~(size_t)255;
+    plan.valid = false;
+    if (!ensure(&plan.dev, &plan.cap, plan.q_off + 256)) return 0;
+    AMTK_CUDA(cudaMemcpyAsync(plan.dev, segs.data(), seg_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    AMTK_CUDA(cudaStreamSynchronize(ctx->stream));
+    plan.nitems = (int)segs.size();
+    plan.wY = wY; plan.hY = hY; plan.wC = wC; plan.hC = hC; plan.nf = nf; plan.f0 = f0; plan.R = 1000 * NS + kMmTH;
     plan.item = ctx->knobs.comb_item; plan.ctas = occ; plan.valid = true;
   }
   AMTK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(plan.dev) + plan.q_off, 0, 256, ctx->stream));
@@ -493,7 +601,7 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
     else { AMTK_CUDA(cudaEventCreate(&ev.first)); AMTK_CUDA(cudaEventCreate(&ev.second)); }
     AMTK_CUDA(cudaEventRecord(ev.first, ctx->stream));
   }
-  V->kernel<<<grid, 32 * kWsWarps, V->smem, ctx->stream>>>(args);
+  kern<<<grid, kMmThreads, smem, ctx->stream>>>(args);
   AMTK_CUDA(cudaGetLastError());
   if (ctx->timing) { AMTK_CUDA(cudaEventRecord(ev.second, ctx->stream)); ctx->timing_events.push_back(ev); }
   ctx->launches += 1;
@@ -533,6 +641,7 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     }
     return 1;
   }
+  if (clip->bytes_per_sample == 1 && ctx->knobs.comb_mma) return launch_comb_mma(ctx, clip, win, lo, hi, prm, dcounts, out_row0);
   if (clip->bytes_per_sample == 1 && ctx->knobs.comb_ws) return launch_comb_ws(ctx, clip, win, lo, hi, prm, dcounts, out_row0);
   const int hY = clip->height, hC = clip->height >> clip->log_uvy;
   const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_comb_R(hY, hC);
@@ -721,6 +830,9 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_LITE_CTAS")) c->knobs.lite_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("AMTK_COMB_WS_STAGES")) c->knobs.comb_ws_stages = atoi(e);
   if (const char* e = getenv("AMTK_COMB_ITEM")) c->knobs.comb_item = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_MMA")) c->knobs.comb_mma = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_WS_WARPS")) c->knobs.comb_ws_warps = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_WS_PF")) c->knobs.comb_ws_prefetch = atoi(e);
   cudaSetDevice(prev);
   if (!ok) { amtk_ctx_destroy(c); return 0; }
   *out = c;

@@ -75,6 +75,9 @@ struct amtk_ctx {
     int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_sync = 0, comb_l2 = 64;
     int comb_item = 0;        // frames per long work item of the warp-stream kernel (0 = auto)
     int comb_ws_stages = 2;  // ring slots per warp stream
+    int comb_mma = 0;        // 1: tensor-core streaming kernel (comb_mma.cuh) for 8-bit clips
+    int comb_ws_warps = 4;   // warp streams per CTA
+    int comb_ws_prefetch = 0; // L2 prefetch distance of the warp streams' tile loads (steps ahead of the slot refill)
     int lite_ctas = 5;      // CTAs per SM of the small-footprint logo kernel when it runs on its own
     int scan_lite = 0;      // fused step: 0 = logo_scores after the comb kernel (default); 1 = logo_lite UNDER the comb kernel on the side
                             // stream (step 1.324 vs 1.339 ms, but the comb kernel itself stretches 1.225 -> 1.309 ms); 2 = logo_lite alone (1.370 ms)

@@ -1,0 +1,364 @@
+// comb_mma.cuh -- field-difference / combing metric, streaming pass, tensor-core variant (8-bit samples).
+//
+// Why tensor cores in an HBM-streaming kernel: the SIMT kernels (comb_kernels.cuh, comb_stream.cuh) are NOT memory bound.
+// They sit at 0.70 of the measured HBM peak because the 5-tap vertical stencil costs ~6 issue slots per pixel
+// (u8 -> fp16 conversion 0.5, stencil 2.0, thresholds 1.0, mask sums 0.5, inter-frame difference 1.25, loads/overhead)
+// and the ALU pipe (HSET2/PRMT/LOP3/IADD3) saturates first (profiles/r02_*).  The stencil is a product with a banded
+// Toeplitz matrix -- exact in u8 x u8 -> s32 -- and the tensor pipe is otherwise idle, so here it does the stencil:
+//
+//     D[x][n] = sum_r  tile[r][x] * band[r][n]          M = 128 pixels of a tile row, K = 64 box rows, N = 128
+//        n in [0,60):    pos(y0+n) = p[y-2] + 4 p[y] + p[y+2]        (band entries 1, 4, 1)
+//        n in [64,124):  neg(y0+n) = 3 (p[y-1] + p[y+1])             (band entries 3, 3)
+//
+// as two tcgen05.mma.kind::i8 (M128 N128 K32) per tile-frame, issued by one thread, with the TMA-staged tile itself as the
+// MN-major A operand (128-byte swizzle: the tile is never copied or converted) and the accumulator in tensor memory.
+// Both halves are < 2048, so their low 16 bits are exact fp16 bit patterns (k * 2^-24): tcgen05.ld ... .pack::16b hands
+// every thread (= one pixel column) its 60 responses as 2 x 30 packed registers, and the rest is
+//     r = HADD2(pos, -neg);  HSET2.GE(|r|, thS);  HSET2.GE(|r|, thL);  3-input adds of the masks
+// = 2 issue slots per pixel for the comb response instead of 4.5.  The two 16-bit lanes of a register are rows y, y+1 =
+// the two fields, so one pair-coded accumulator carries both field counters.  The inter-frame difference stays on the
+// SIMT side (VABSDIFF4 + SWAR compare + IDP.4A on the raw bytes of the current and the previous slot).
+//
+// Same integer spec, same counters, bit-identical results (integer adds commute).  One CTA (4 warps) = one tile stream;
+// 4 CTAs per SM (4 x 128 tensor-memory columns = all 512).
+#pragma once
+#include <cuda_fp16.h>
+#include "amtk_internal.h"
+#include "tma_utils.cuh"
+#include "comb_stream.cuh"       // WsArgs / WsClass / CombSegment / bytes_ge
+
+namespace amtk {
+
+constexpr int kMmTW = 128;                       // tile width in bytes = MMA M
+constexpr int kMmTH = 60;                        // output rows per tile
+constexpr int kMmBoxH = 64;                      // + 2 halo rows above and below = MMA K
+constexpr int kMmSlot = kMmTW * kMmBoxH;         // 8192 bytes
+constexpr int kMmStages = 4;                     // previous frame, current frame, two frames in flight (power of two)
+constexpr int kMmConsumerWarps = 4;
+constexpr int kMmThreads = 32 * (kMmConsumerWarps + 1);   // + the producer warp
+constexpr int kMmBandBytes = 128 * kMmBoxH;      // N x K u8
+constexpr int kMmSmemPerStream = kMmStages * kMmSlot;    // + kMmBandBytes + 1024 once per CTA   // + slack for the 1024-byte alignment the swizzle needs
+constexpr int kMmBandLBO = 2048, kMmBandSBO = 128;                   // band matrix: K-major, no swizzle, 8x16-byte core matrices
+
+// ---- tcgen05 wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], u8 x u8 -> s32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// 32 lanes x 32 columns, low 16 bits of each column, two adjacent columns per register (even column in the low half)
+__device__ __forceinline__ void tc_ld_pack16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {        // one 32-bit column of this thread's lane
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+
+// shared-memory matrix descriptor (sm_100 format: version 1 at bit 46)
+__device__ __forceinline__ uint64_t mm_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+// instruction descriptor: D = s32, A = u8 MN-major, B = u8 K-major, M = 128, N = 128, dense, no saturation
+constexpr uint32_t kMmIdesc = (2u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (0u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// band[n][k], k = box row (global row y0 - 2 + k), n = output column of D
+__device__ __forceinline__ uint32_t mm_band(int n, int k) {
+  if (n < kMmTH) { const int d = k - n; return (d == 0 || d == 4) ? 1u : (d == 2 ? 4u : 0u); }
+  if (n >= 64 && n < 64 + kMmTH) { const int d = k - (n - 64); return (d == 1 || d == 3) ? 3u : 0u; }
+  return 0u;
+}
+
+// Roles: warps 0..3 = consumers (warp w owns tensor-memory lanes 32w..32w+31 = 32 pixel columns of each tile, and 15 of
+// the 60 strip rows of the inter-frame difference); warp 4 = producer (TMA loads, MMA issue, counter flush).
+// A CTA streams TWO tiles at once (work items come in pairs with the same frame range): every step loads, multiplies and
+// thresholds frame k of both tiles, so the fixed per-step costs (two mbarrier waits, the accumulator hand-over, loop and
+// ring bookkeeping) are paid once per two tile-frames, and a consumer warp has ~500 independent instructions between
+// handing the accumulators back and needing the next ones -- that is what hides the ~800-cycle MMA round trip.
+// No block barrier in the frame loop: consumers wait only for data (full_bar, mma_bar); the producer waits for free_bar,
+// on which every consumer warp arrives once both accumulators of step k are in its registers and it is done with the
+// slots of step k-1.  2 CTAs per SM (2 x 256 tensor-memory columns = all 512).
+template <int NS>
+__global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __grid_constant__ WsArgs a) {
+  constexpr int kStageBytes = NS * kMmSlot;
+  constexpr int kTmemCols = 128 * NS;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMmStages];
+  __shared__ __align__(8) uint64_t mma_bar, free_bar;
+  __shared__ uint32_t tmem_holder;
+  __shared__ int item_s;
+  __shared__ uint32_t red[4][16];                            // [step & 3][stream * 8 + counter]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == kMmConsumerWarps;
+  uint8_t* slots = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* band = slots + kMmStages * kStageBytes;
+
+  // ---- one-time setup: tensor memory, band matrix, barriers ----
+  if (producer) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"((uint32_t)kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int o = tid * 4; o < kMmBandBytes; o += kMmThreads * 4) {       // 4 consecutive k of one row n per store
+    const int kc = o / kMmBandLBO, rem = o - kc * kMmBandLBO;
+    const int ng = rem / kMmBandSBO, i = (rem % kMmBandSBO) >> 4, kk = rem & 15;
+    const int n = ng * 8 + i, k = kc * 16 + kk;
+    *reinterpret_cast<uint32_t*>(band + o) = mm_band(n, k) | (mm_band(n, k + 1) << 8) | (mm_band(n, k + 2) << 16) | (mm_band(n, k + 3) << 24);
+  }
+  if (tid < 64) red[tid >> 4][tid & 15] = 0u;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kMmStages; ++s) mbar_init(&full_bar[s], 1);
+    mbar_init(&mma_bar, 1);
+    mbar_init(&free_bar, kMmConsumerWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // band matrix: generic-proxy stores -> async-proxy (MMA) reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 lanes
+  const uint32_t slots_u32 = smem_u32(slots);
+  const uint64_t descB0 = mm_desc(smem_u32(band), kMmBandLBO, kMmBandSBO, 0u);
+  const uint64_t descB1 = mm_desc(smem_u32(band) + 2 * kMmBandLBO, kMmBandLBO, kMmBandSBO, 0u);
+
+  // inter-frame difference: consumer thread t < 120 owns strip (t & 7) of tile rows 4g .. 4g+3, g = t >> 3; its four
+  // 16-byte chunks sit at these offsets of a slot (128-byte swizzle: chunk index ^ (row & 7))
+  const bool mv_active = tid < (kMmTH / 4) * 8;
+  int mv_off[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const int b = 2 + 4 * (tid >> 3) + i; mv_off[i] = b * kMmTW + (((tid & 7) ^ (b & 7)) << 4); }
+
+  uint32_t gload = 0;          // stage loads consumed so far (ring position)
+  uint32_t nmma = 0;           // MMA batches committed so far (phase of mma_bar)
+  uint32_t nfree = 0;          // completed phases of free_bar (producer)
+  for (;;) {
+    if (tid == kMmConsumerWarps * 32) item_s = atomicAdd(a.queue, 1);
+    __syncthreads();
+    // warp-uniform by construction; the reduction tells the compiler so (uniform registers for all the bookkeeping)
+    const int pair = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)item_s);
+    if (NS * pair >= a.nitems) break;
+    int tileS[NS], fb = 0, fe = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const CombSegment seg = a.segs[NS * pair + s];
+      tileS[s] = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(seg.tile + 0x40000000)) - 0x40000000;   // < 0: filler stream, results dropped
+      if (s == 0) { fb = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)seg.fbegin); fe = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)seg.fend); }
+    }
+    const int nf = fe - fb;
+    const int nloads = nf + 1;                               // L_0 = previous frame, L_k = frame fb+k-1
+    const int fprev = fb > 0 ? fb - 1 : fb;
+    int ciS[NS], txS[NS], y0S[NS]; bool dropS[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      dropS[s] = tileS[s] < 0;
+      const int tile = dropS[s] ? ~tileS[s] : tileS[s];
+      int ci = 0;
+#pragma unroll
+      for (int k = 1; k < kWsMaxClasses; ++k) if (k < a.nclasses && tile >= a.cl[k].tile0) ci = k;
+      const int lt = tile - a.cl[ci].tile0;
+      const int ty = lt / a.cl[ci].tilesX;
+      ciS[s] = ci; txS[s] = lt - ty * a.cl[ci].tilesX; y0S[s] = ty * kMmTH;
+    }
+
+    if (producer) {
+      // =========================== producer warp ===========================
+      auto issue_load = [&](int j) {                         // lane 0 only: both tiles of load j into one stage
+        const uint32_t gl = gload + (uint32_t)j;
+        const int st = (int)(gl & (kMmStages - 1));
+        const int fr = (j == 0) ? fprev : fb + j - 1;
+        mbar_expect_tx(&full_bar[st], kStageBytes);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          tma_load_3d(slots + st * kStageBytes + s * kMmSlot, &a.map[a.cl[ciS[s]].map], &full_bar[st], txS[s] * kMmTW, y0S[s] - 2, fr);
+      };
+      auto issue_mma = [&](int j) {                          // all lanes wait for the stage, lane 0 issues
+        const uint32_t gl = gload + (uint32_t)j;
+        const int st = (int)(gl & (kMmStages - 1));
+        mbar_wait(&full_bar[st], (gl / kMmStages) & 1u);
+        if (lane == 0) {
+          tc_fence_after();
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            const uint32_t sa = slots_u32 + st * kStageBytes + s * kMmSlot;
+            tc_mma_i8(tmem_base + s * 128u, mm_desc(sa, 0u, 1024u, 2u), descB0, kMmIdesc, 0u);                 // box rows 0..31
+            tc_mma_i8(tmem_base + s * 128u, mm_desc(sa + 32 * kMmTW, 0u, 1024u, 2u), descB1, kMmIdesc, 1u);    // box rows 32..63
+          }
+          tc_commit(&mma_bar);
+        }
+        __syncwarp();
+      };
+      const int fl_s = lane >> 3, fl_i = lane & 7;           // flush lane = (stream, counter)
+      int* const crow = (lane < 8 * NS && fl_i < 6 && !dropS[fl_s & (NS - 1)])
+                            ? a.counts + a.cl[ciS[fl_s & (NS - 1)]].cls * 6 + fl_i + ((long long)fb - 1 - a.out_frame0) * 12 : nullptr;
+      auto flush = [&](int k) {                              // counters of frame k: shared -> global, slot cleared for reuse
+        if (lane < 8 * NS) {
+          const uint32_t v = red[k & 3][lane];
+          red[k & 3][lane] = 0u;
+          if (crow && v) atomicAdd(crow + (size_t)k * 12, (int)v);
+        }
+      };
+      if (lane == 0) {
+        const int pro = nloads < kMmStages ? nloads : kMmStages;
+        for (int j = 0; j < pro; ++j) issue_load(j);
+      }
+      __syncwarp();
+      issue_mma(1);
+      for (int k = 1; k <= nf; ++k) {
+        mbar_wait_sleep(&free_bar, nfree & 1u); ++nfree;     // accumulators of step k are in registers; stage of load k-1 is free
+        if (lane == 0 && (k + kMmStages - 1) < nloads) issue_load(k + kMmStages - 1);
+        if (k < nf) issue_mma(k + 1);
+        if (k > 1) flush(k - 1);                             // every consumer published frame k-1 before it arrived for step k
+      }
+      mbar_wait_sleep(&free_bar, nfree & 1u); ++nfree;       // the consumers' closing arrival: frame nf is published
+      flush(nf);
+      nmma += (uint32_t)nf;
+    } else {
+      // =========================== consumer warps ===========================
+      // rows of a tile the spec excludes although the plain pass counts them: y < 2 and H-2 <= y < H+2 (rows >= H are
+      // zero-filled by TMA, but the windows of H, H+1 still see the last two real rows).  Bit n = tile row n.
+      unsigned long long fixS[NS];
+      uint32_t kMS[NS], tSS[NS], tLS[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const WsClass& C = a.cl[ciS[s]];
+        unsigned long long fix = 0ull;
+        if (y0S[s] == 0) fix |= 3ull;
+        const int lo = max(C.H - 2 - y0S[s], 0), hi = min(C.H + 2 - y0S[s], kMmTH);
+        if (hi > lo) fix |= ((1ull << hi) - 1ull) & ~((1ull << lo) - 1ull);
+        fixS[s] = fix; kMS[s] = C.thM; tSS[s] = C.thS; tLS[s] = C.thL;
+      }
+      const bool any_fix = (fixS[0] | fixS[NS - 1]) != 0ull;
+
+      // inter-frame difference of load j against load j-1, one tile: packed hits, low half = even rows, high = odd rows
+      auto move_tile = [&](const uint8_t* cur, const uint8_t* prv, uint32_t kM) -> uint32_t {
+        uint32_t cM0 = 0u, cM1 = 0u;
+        if (mv_active) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 c4 = *reinterpret_cast<const uint4*>(cur + mv_off[i]);
+            const uint4 p4 = *reinterpret_cast<const uint4*>(prv + mv_off[i]);
+            uint32_t& m = (i & 1) ? cM1 : cM0;
+            m = __dp4a(bytes_ge(__vabsdiffu4(c4.x, p4.x), kM), 0x01010101u, m);
+            m = __dp4a(bytes_ge(__vabsdiffu4(c4.y, p4.y), kM), 0x01010101u, m);
+            m = __dp4a(bytes_ge(__vabsdiffu4(c4.z, p4.z), kM), 0x01010101u, m);
+            m = __dp4a(bytes_ge(__vabsdiffu4(c4.w, p4.w), kM), 0x01010101u, m);
+          }
+        }
+        return (cM0 >> 7) | ((cM1 >> 7) << 16);               // <= 32 hits per half and lane
+      };
+      auto move_step = [&](int j, uint32_t (&pend)[NS]) {
+        const uint32_t gl = gload + (uint32_t)j;
+        const int st = (int)(gl & (kMmStages - 1)), sp = (int)((gl - 1) & (kMmStages - 1));
+        mbar_wait(&full_bar[st], (gl / kMmStages) & 1u);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          pend[s] = move_tile(slots + st * kStageBytes + s * kMmSlot, slots + sp * kStageBytes + s * kMmSlot, kMS[s]);
+      };
+      // thresholds of one accumulator (this thread's pixel column, 64 columns = 32 row pairs each of pos and neg)
+      auto comb_tile = [&](const uint32_t (&pos)[32], const uint32_t (&neg)[32], uint32_t tS, uint32_t tL, uint32_t& accS, uint32_t& accL) {
+        const __half2 thS = *reinterpret_cast<const __half2*>(&tS);
+        const __half2 thL = *reinterpret_cast<const __half2*>(&tL);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t mS[16], mL[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const __half2 r = __habs2(__hsub2(*reinterpret_cast<const __half2*>(&pos[16 * h + q]), *reinterpret_cast<const __half2*>(&neg[16 * h + q])));
+            mS[q] = __hge2_mask(r, thS);
+            mL[q] = __hge2_mask(r, thL);
+          }
+          accS = accS - (mS[0] + mS[1]) - (mS[2] + mS[3] + mS[4]) - (mS[5] + mS[6] + mS[7]) - (mS[8] + mS[9] + mS[10]) - (mS[11] + mS[12] + mS[13]) - (mS[14] + mS[15]);
+          accL = accL - (mL[0] + mL[1]) - (mL[2] + mL[3] + mL[4]) - (mL[5] + mL[6] + mL[7]) - (mL[8] + mL[9] + mL[10]) - (mL[11] + mL[12] + mL[13]) - (mL[14] + mL[15]);
+        }
+      };
+
+      {                                                      // L_0: the frame before the first one of this item
+        const int st = (int)(gload & (kMmStages - 1));
+        mbar_wait(&full_bar[st], (gload / kMmStages) & 1u);
+      }
+      uint32_t pendM[NS];
+      move_step(1, pendM);
+      for (int k = 1; k <= nf; ++k) {
+        mbar_wait(&mma_bar, nmma & 1u); ++nmma;              // both accumulators of step k are complete
+        tc_fence_after();
+        uint32_t pos[NS][32], neg[NS][32];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          tc_ld_pack16(tmem_lane + s * 128u, *reinterpret_cast<uint32_t(*)[16]>(&pos[s][0]));
+          tc_ld_pack16(tmem_lane + s * 128u + 32u, *reinterpret_cast<uint32_t(*)[16]>(&pos[s][16]));
+          tc_ld_pack16(tmem_lane + s * 128u + 64u, *reinterpret_cast<uint32_t(*)[16]>(&neg[s][0]));
+          tc_ld_pack16(tmem_lane + s * 128u + 96u, *reinterpret_cast<uint32_t(*)[16]>(&neg[s][16]));
+        }
+        uint32_t fixv[NS] = {};                       // edge tiles: hits of the excluded rows, packed [S even | S odd<<8 | L even<<16 | L odd<<24]
+        if (any_fix) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            const int thS_i = (int)(tSS[s] & 0xFFFFu), thL_i = (int)(tLS[s] & 0xFFFFu);
+            for (unsigned long long m = fixS[s]; m; m &= m - 1ull) {
+              const int n = __ffsll((long long)m) - 1;
+              const int pv = (int)tc_ld1(tmem_lane + s * 128u + (uint32_t)n), nv = (int)tc_ld1(tmem_lane + s * 128u + 64u + (uint32_t)n);
+              tc_wait_ld();
+              const int r = abs(pv - nv);
+              fixv[s] += ((r >= thS_i) ? 1u : 0u) << ((n & 1) * 8);
+              fixv[s] += ((r >= thL_i) ? 1u : 0u) << (16 + (n & 1) * 8);
+            }
+          }
+        }
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&free_bar);               // accumulators and the stage of load k-1 may be overwritten
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          uint32_t accS = 0u, accL = 0u;                     // pair-coded: low half = even rows (top field), high = odd rows
+          comb_tile(pos[s], neg[s], tSS[s], tLS[s], accS, accL);
+          // warp totals; decode of the pair code: low half = hits in even rows, high half = (odd - even) mod 2^16
+          const uint32_t rS = __reduce_add_sync(0xFFFFFFFFu, accS), rL = __reduce_add_sync(0xFFFFFFFFu, accL);
+          const uint32_t rM = __reduce_add_sync(0xFFFFFFFFu, pendM[s]);
+          // counts[] layout of one class: [field][move, shima, lshima]; lane i < 6 publishes counter i
+          const uint32_t src = (lane == 0 || lane == 3) ? rM : ((lane == 1 || lane == 4) ? rS : rL);
+          uint32_t v = lane < 3 ? (src & 0xFFFFu) : ((lane == 3 ? (src >> 16) : ((src >> 16) + src)) & 0xFFFFu);
+          if (any_fix) {
+            // lanes spread the 8-bit fields over 4 words of 32 lanes: sums stay < 256 per field only if <= 7 hits per lane
+            const uint32_t fS = __reduce_add_sync(0xFFFFFFFFu, fixv[s] & 0xFFFFu), fL = __reduce_add_sync(0xFFFFFFFFu, fixv[s] >> 16);
+            // per lane <= 4 excluded rows -> <= 4 hits per 8-bit field... x 32 lanes = 128 < 256
+            if (lane == 1) v -= fS & 0xFFu;
+            if (lane == 4) v -= (fS >> 8) & 0xFFu;
+            if (lane == 2) v -= fL & 0xFFu;
+            if (lane == 5) v -= (fL >> 8) & 0xFFu;
+          }
+          if (lane < 6 && v) atomicAdd(&red[k & 3][s * 8 + lane], v);
+        }
+        if (k < nf) move_step(k + 1, pendM);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&free_bar);                 // closing arrival: the counters of frame nf are published
+    }
+    gload += (uint32_t)nloads;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (producer) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+}
+
+}  // namespace amtk

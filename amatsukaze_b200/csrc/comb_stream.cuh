@@ -31,17 +31,18 @@ namespace amtk {
 
 constexpr int kWsTW = 128;               // tile width in bytes
 constexpr int kWsRuns = 4;               // runs per warp (8 lanes x 16 bytes per row)
-constexpr int kWsWarps = 4;              // independent warp streams per CTA: one per SM sub-partition
+constexpr int kWsWarps = 4;              // default warp streams per CTA: one per SM sub-partition
 
-template <int R_, int STAGES_>
+template <int R_, int STAGES_, int WARPS_ = kWsWarps>
 struct WsCfg {
-  static constexpr int R = R_, STAGES = STAGES_;
+  static constexpr int R = R_, STAGES = STAGES_, WARPS = WARPS_;
   static constexpr int TH = kWsRuns * R;                    // output rows per tile
   static constexpr int BOXH = TH + 4;                       // + 2 halo rows above and below
   static constexpr int STAGE_BYTES = kWsTW * BOXH;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;   // one warp's ring
-  static constexpr int SMEM = kWsWarps * RING_BYTES + 128;  // + alignment slack
-  static constexpr int MIN_CTAS = (227 * 1024) / (SMEM + 1024 + 64) >= 4 ? 4 : (227 * 1024) / (SMEM + 1024 + 64) >= 3 ? 3 : 2;     // resident CTAs the register budget is set for
+  static constexpr int SMEM = WARPS * RING_BYTES + 128;     // + alignment slack
+  static constexpr int FIT = (227 * 1024) / (SMEM + 1024 + 8 * WARPS * STAGES + 8);    // CTAs that fit in shared memory
+  static constexpr int MIN_CTAS = FIT >= 4 ? 4 : FIT >= 3 ? 3 : FIT >= 2 ? 2 : 1;      // resident CTAs the register budget is set for
 };
 
 // A tile class: all tiles of one class have the same shape and are numbered consecutively from tile0.
@@ -70,6 +71,7 @@ struct WsArgs {
   int* queue;                 // global item counter (zeroed by the host before the launch)
   int* counts;                // [nframes_out][12]
   int out_frame0;
+  int prefetch;               // > 0: tile loads are announced to L2 (cp.async.bulk.prefetch.tensor) this many steps before their slot frees
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -77,6 +79,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 #ifndef AMTK_WS_RELOAD_PREV
@@ -176,6 +185,72 @@ __device__ __forceinline__ WsCounts ws_rows(const uint8_t* __restrict__ cur, uin
   return c;
 }
 
+
+// Software-pipelined form of ws_rows: the thresholds / mask sums of row j-1 (ALU pipe) are written next to the stencil
+// of row j (FMA-heavy pipe), per register pair, so that independent work for both half-rate pipes is adjacent in the
+// instruction stream.  Same results (integer counters).
+__device__ __forceinline__ void ws_masks_q(const __half2 r, const __half2 thS, const __half2 thL, uint32_t& mS, uint32_t& mL) {
+  mS = __hge2_mask(__habs2(r), thS);
+  mL = __hge2_mask(__habs2(r), thL);
+}
+template <int R, int PITCH>
+__device__ __forceinline__ WsCounts ws_rows_sp(const uint8_t* __restrict__ cur, uint4 (&P)[R],
+                                               const uint32_t kM, const uint32_t thS_bits, const uint32_t thL_bits) {
+  const __half2 thS = *reinterpret_cast<const __half2*>(&thS_bits);
+  const __half2 thL = *reinterpret_cast<const __half2*>(&thL_bits);
+  const __half2 k4 = __float2half2_rn(4.0f), km3 = __float2half2_rn(-3.0f);
+  WsCounts c = { { 0u, 0u }, { 0u, 0u }, { 0u, 0u } };
+  H8 h0 = bytes16_to_half(*reinterpret_cast<const uint4*>(cur));
+  H8 h1 = bytes16_to_half(*reinterpret_cast<const uint4*>(cur + PITCH));
+  uint4 raw_c = *reinterpret_cast<const uint4*>(cur + 2 * PITCH);
+  uint4 raw_n = *reinterpret_cast<const uint4*>(cur + 3 * PITCH);
+  H8 h2 = bytes16_to_half(raw_c);
+  H8 h3 = bytes16_to_half(raw_n);
+  __half2 rp[8];                                              // responses of the previous row, not yet thresholded
+#pragma unroll
+  for (int j = 0; j <= R; ++j) {
+    uint4 raw_nn = make_uint4(0u, 0u, 0u, 0u);
+    H8 h4;
+    if (j < R) {
+      raw_nn = *reinterpret_cast<const uint4*>(cur + (j + 4) * PITCH);
+      const uint4 pv = P[j];
+      const int f = j & 1;
+      h4 = bytes16_to_half(raw_nn);
+      c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.x, pv.x), kM), 0x01010101u, c.M[f]);
+      c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.y, pv.y), kM), 0x01010101u, c.M[f]);
+      c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.z, pv.z), kM), 0x01010101u, c.M[f]);
+      c.M[f] = __dp4a(bytes_ge(__vabsdiffu4(raw_c.w, pv.w), kM), 0x01010101u, c.M[f]);
+      if (kWsReloadPrev) P[j] = lds128(cur + (j + 2) * PITCH); else P[j] = raw_c;
+    }
+    uint32_t mS[8], mL[8];
+    __half2 rn[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (j < R) {
+        __half2 t = __hadd2(h0.v[q], h4.v[q]);
+        t = __hfma2(k4, h2.v[q], t);
+        const __half2 u = __hadd2(h1.v[q], h3.v[q]);
+        rn[q] = __hfma2(km3, u, t);
+      }
+      if (j > 0) ws_masks_q(rp[q], thS, thL, mS[q], mL[q]);
+    }
+    if (j > 0) {
+      const int fp = (j - 1) & 1;
+      c.S[fp] = c.S[fp] - (mS[0] + mS[1]) - (mS[2] + mS[3] + mS[4]) - (mS[5] + mS[6] + mS[7]);
+      c.L[fp] = c.L[fp] - (mL[0] + mL[1]) - (mL[2] + mL[3] + mL[4]) - (mL[5] + mL[6] + mL[7]);
+    }
+    if (j < R) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rp[q] = rn[q];
+      h0 = h1; h1 = h2; h2 = h3; h3 = h4; raw_c = raw_n; raw_n = raw_nn;
+    }
+  }
+  return c;
+}
+
+#ifndef AMTK_WS_SP
+#define AMTK_WS_SP 0
+#endif
 // Rows the spec excludes from the comb response but the plain body counted: y < 2, H-2 <= y < H (no full window) and
 // the phantom rows H, H+1 (zero-filled by TMA; their windows still see the last two real rows).  The affected lanes
 // re-evaluate exactly those rows and ADD the masks back (the body subtracted them).  Rare: edge tiles only, and then
@@ -200,10 +275,10 @@ __device__ __noinline__ void ws_fixup(const uint8_t* cur, uint32_t rows, uint32_
 }
 
 template <typename Cfg>
-__global__ void __launch_bounds__(32 * kWsWarps, Cfg::MIN_CTAS) comb_ws_kernel(const __grid_constant__ WsArgs a) {
+__global__ void __launch_bounds__(32 * Cfg::WARPS, Cfg::MIN_CTAS) comb_ws_kernel(const __grid_constant__ WsArgs a) {
   constexpr int S = Cfg::STAGES, R = Cfg::R;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bars[kWsWarps][S];
+  __shared__ __align__(8) uint64_t full_bars[Cfg::WARPS][S];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* tiles = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + warp * Cfg::RING_BYTES;   // this warp's ring
   uint64_t* full_bar = full_bars[warp];
@@ -243,9 +318,16 @@ __global__ void __launch_bounds__(32 * kWsWarps, Cfg::MIN_CTAS) comb_ws_kernel(c
       if (C.kind == 0) tma_load_3d(dst, &a.map[C.map], &full_bar[st], tx * kWsTW, y0 - 2, fr);
       else tma_load_4d(dst, &a.map_uv, &full_bar[st], C.x0, 0, y0 - 2, fr);
     };
+    auto prefetch_at = [&](int j) {                          // lane 0 only: pull load j (a frame of this tile) into L2
+      const int fr = seg.fbegin + j - 1;                     // j >= S >= 1
+      if (C.kind == 0) tma_prefetch_3d(&a.map[C.map], tx * kWsTW, y0 - 2, fr);
+      else tma_prefetch_4d(&a.map_uv, C.x0, 0, y0 - 2, fr);
+    };
+    const int pf = a.prefetch;
     if (lane == 0) {
       const int pro = nloads < S ? nloads : S;
       for (int j = 0; j < pro; ++j) issue_at(j, (int)((gload + (uint32_t)j) % S));
+      for (int j = S; j < S + pf && j < nloads; ++j) prefetch_at(j);
     }
     // rows of this lane's run the spec excludes (bit j = row y_first + j)
     uint32_t fix_mine = 0u;
@@ -269,12 +351,13 @@ __global__ void __launch_bounds__(32 * kWsWarps, Cfg::MIN_CTAS) comb_ws_kernel(c
       for (int j = 0; j < R; ++j) P[j] = *reinterpret_cast<const uint4*>(l0 + (j + 2) * kWsTW);
       __syncwarp();
       if (lane == 0 && S < nloads) issue_at(S, st);          // its slot is free again at once: the rows live in registers
+      if (lane == 0 && pf > 0 && S + pf < nloads) prefetch_at(S + pf);
     }
     for (int k = 1; k <= nf; ++k) {
       if (++st == S) { st = 0; ph ^= 1u; }
       mbar_wait(&full_bar[st], ph);
       const uint8_t* cur = tiles + st * Cfg::STAGE_BYTES + lane_off;
-      WsCounts c = ws_rows<R, kWsTW>(cur, P, kM, tS, tL);
+      WsCounts c = AMTK_WS_SP ? ws_rows_sp<R, kWsTW>(cur, P, kM, tS, tL) : ws_rows<R, kWsTW>(cur, P, kM, tS, tL);
       if (fix_rows) {
         ws_fixup<kWsTW>(cur, fix_rows, fix_mine, tS, tL, c);
         __syncwarp();
@@ -287,6 +370,7 @@ __global__ void __launch_bounds__(32 * kWsWarps, Cfg::MIN_CTAS) comb_ws_kernel(c
       const uint32_t rM1 = __reduce_add_sync(0xFFFFFFFFu, m1), rS1 = __reduce_add_sync(0xFFFFFFFFu, s1), rL1 = __reduce_add_sync(0xFFFFFFFFu, l1);
       __syncwarp();                                          // every lane is past its shared-memory reads of this slot
       if (lane == 0 && (k + S) < nloads) issue_at(k + S, st);               // refill the slot that was just released
+      if (lane == 0 && pf > 0 && (k + S + pf) < nloads) prefetch_at(k + S + pf);
       if (lane < 6) {                                        // lane = field*3 + metric = the counts[] layout of one class
         const int fld = lane >= 3, met = lane - 3 * fld;
         uint32_t v = met == 0 ? (fld ? rM1 : rM0) : met == 1 ? (fld ? rS1 : rS0) : (fld ? rL1 : rL0);

@@ -279,3 +279,53 @@ def test_fused_step_with_coresident_logo_kernel(oracle, monkeypatch, mode):
         assert np.array_equal(_bits(s10.cpu().numpy()[:, 0]), _bits(rs10))
     finally:
         c.close()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("variant", ["ws", "cta_ring", "mma1", "mma2"])
+def test_every_comb_kernel_variant_is_bit_exact(oracle, monkeypatch, variant):
+    """The streaming pass exists in four forms: the default warp-stream kernel (comb_stream.cuh), the round-1 CTA-ring kernel
+    (comb_kernels.cuh, AMTK_COMB_WS=0) and the two tensor-core forms (comb_mma.cuh: stencil as tcgen05.mma.kind::i8 with the
+    TMA-staged tile as the MN-major operand; AMTK_COMB_MMA=1: one tile per CTA step, =2: two).  All must return the spec
+    oracle's counters bit for bit: ragged shapes (partial tile columns and rows, planes smaller than a tile, odd tile
+    counts -> filler stream), extreme thresholds, edge rows, frame-range calls with a halo frame, and configs[1]/[2]
+    geometry."""
+    po = oracle
+    env = {"ws": {}, "cta_ring": {"AMTK_COMB_WS": "0"}, "mma1": {"AMTK_COMB_MMA": "1"}, "mma2": {"AMTK_COMB_MMA": "2"}}[variant]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = ab.Context(0, torch.cuda.current_stream().cuda_stream)
+    for k in env:
+        monkeypatch.delenv(k)
+    try:
+        prm = ab.default_comb_params()
+        prm.th_move_y, prm.th_shima_y, prm.th_lshima_y = 1, 1, 2047
+        prm.th_move_c, prm.th_shima_c, prm.th_lshima_c = 128, 700, 701
+        for (w, h, n) in ((160, 34, 3), (128, 272, 5), (1952, 36, 2), (32, 1100, 2), (640, 360, 9)):
+            fr = synth.make_frames(3, n, w, h, device="cuda", mode="interlaced")
+            out = c.comb_frames(ab.yv12_clip(fr, w, h, n, True), prm).cpu().numpy()
+            Y, U, V = synth.split_planes(fr, w, h)
+            assert np.array_equal(out, po.or_comb_clip(Y, U, V, prm.as_list())), (variant, w, h)
+        # maximum response everywhere: alternating 0 / 255 rows
+        w, h = 256, 128
+        fr = torch.zeros((2, w * h * 3 // 2), dtype=torch.uint8, device="cuda")
+        fr[:, : w * h].view(2, h, w)[:, 0::2, :] = 255
+        p2 = ab.default_comb_params()
+        p2.th_shima_y, p2.th_lshima_y = 1530, 1531
+        out = c.comb_frames(ab.yv12_clip(fr, w, h, 2, True), p2).cpu().numpy()
+        assert out[0, 1] + out[0, 4] == (h - 4) * w and out[0, 2] + out[0, 5] == 0 and out[:, 0].sum() == 0
+        # BASELINE geometries with default thresholds, whole call and two range calls (halo frame)
+        prm = ab.default_comb_params()
+        for (w, h, n) in ((1920, 1080, 40), (1440, 1080, 18)):
+            f8 = _gen(3, n, w, h, mode="telecine")
+            clip = ab.yv12_clip(f8, w, h, n, True)
+            got = c.comb_frames(clip, prm).cpu().numpy()
+            Y, U, V = synth.split_planes(f8, w, h)
+            ref = np.stack([po.or_comb_frame((Y[i], U[i], V[i]), (Y[max(i - 1, 0)], U[max(i - 1, 0)], V[max(i - 1, 0)]), prm.as_list(), "avx2")
+                            for i in range(n)])
+            assert np.array_equal(got, ref), (variant, w, h, np.argwhere(got != ref)[:5])
+            part = np.concatenate([c.comb_frames(clip, prm, 0, 7).cpu().numpy(), c.comb_frames(clip, prm, 7, n - 7).cpu().numpy()])
+            assert np.array_equal(part, ref), (variant, w, h, "ranges")
+            assert ref[:, [1, 4]].sum() > 0 and ref[1:, 0].sum() > 0
+    finally:
+        c.close()
