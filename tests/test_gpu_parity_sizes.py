@@ -267,7 +267,8 @@ def test_fused_step_with_coresident_logo_kernel(oracle, monkeypatch, mode):
         rs = np.stack([o.scan_frame(Y[i]) for i in range(n)])
         rc = po.or_comb_clip(Y, U, V, prm.as_list())
         assert np.array_equal(_bits(s.cpu().numpy()[:, 0]), _bits(rs)) and np.array_equal(cn.cpu().numpy(), rc)
-        s2, c2 = c.scan_comb_frames(ab.yv12_clip(f8.cpu().numpy(), w, h, n, False), [logo], prm)
+        h8 = f8.cpu().numpy()                               # the descriptor holds a raw pointer: keep the array alive
+        s2, c2 = c.scan_comb_frames(ab.yv12_clip(h8, w, h, n, False), [logo], prm)
         assert np.array_equal(_bits(s2[:, 0]), _bits(rs)) and np.array_equal(c2, rc)
         f16 = (f8.to(torch.int32) * 4 + (f8.to(torch.int32) & 3)).to(torch.int16).contiguous()
         p10 = ab.default_comb_params()
