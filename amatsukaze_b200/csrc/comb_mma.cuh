@@ -141,12 +141,19 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
   const uint64_t descB0 = mm_desc(smem_u32(band), kMmBandLBO, kMmBandSBO, 0u);
   const uint64_t descB1 = mm_desc(smem_u32(band) + 2 * kMmBandLBO, kMmBandLBO, kMmBandSBO, 0u);
 
-  // inter-frame difference: consumer thread t < 120 owns strip (t & 7) of tile rows 4g .. 4g+3, g = t >> 3; its four
-  // 16-byte chunks sit at these offsets of a slot (128-byte swizzle: chunk index ^ (row & 7))
-  const bool mv_active = tid < (kMmTH / 4) * 8;
-  int mv_off[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { const int b = 2 + 4 * (tid >> 3) + i; mv_off[i] = b * kMmTW + (((tid & 7) ^ (b & 7)) << 4); }
+  // inter-frame difference: consumer thread t owns strip (t & 7) of the box rows b0, b0+8, b0+16, b0+24 with
+  // b0 = 2 + (t >> 3) for t < 64 and 34 + ((t - 64) >> 3) for the rest (rows 2..61 = the 60 tile rows; the fourth row of
+  // the last four row groups would be 62..65 and is skipped).  Rows 8 apart share (row & 7), so the swizzled 16-byte chunk
+  // (chunk index ^ (row & 7)) is the same in all four: one address + immediates.  They also share the row parity = the field.
+  const int mv_b0 = (tid < 64 ? 2 : 34) + ((tid & 63) >> 3);
+  const int mv_toff = mv_b0 * kMmTW + (((tid & 7) ^ (mv_b0 & 7)) << 4);
+  const bool mv_row3 = mv_b0 + 24 <= kMmTH + 1;
+  const int mv_shift = (mv_b0 & 1) ? 16 : 0;                 // tile row = box row - 2: same parity; odd rows count in the high half
+  // publishing lane i < 6 of a consumer warp owns counter i of counts[]' [field][move, shima, lshima] layout
+  const uint32_t pub_selM = (lane == 0 || lane == 3) ? 0xFFFFFFFFu : 0u, pub_selS = (lane == 1 || lane == 4) ? 0xFFFFFFFFu : 0u;
+  const uint32_t pub_selL = (lane == 2 || lane == 5) ? 0xFFFFFFFFu : 0u;
+  const int pub_shift = (lane >= 3 && lane < 6) ? 16 : 0;
+  uint32_t* const pub_red = &red[0][lane & 7];
 
   uint32_t gload = 0;          // stage loads consumed so far (ring position)
   uint32_t nmma = 0;           // MMA batches committed so far (phase of mma_bar)
@@ -251,20 +258,18 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
 
       // inter-frame difference of load j against load j-1, one tile: packed hits, low half = even rows, high = odd rows
       auto move_tile = [&](const uint8_t* cur, const uint8_t* prv, uint32_t kM) -> uint32_t {
-        uint32_t cM0 = 0u, cM1 = 0u;
-        if (mv_active) {
+        uint32_t m = 0u;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 c4 = *reinterpret_cast<const uint4*>(cur + mv_off[i]);
-            const uint4 p4 = *reinterpret_cast<const uint4*>(prv + mv_off[i]);
-            uint32_t& m = (i & 1) ? cM1 : cM0;
-            m = __dp4a(bytes_ge(__vabsdiffu4(c4.x, p4.x), kM), 0x01010101u, m);
-            m = __dp4a(bytes_ge(__vabsdiffu4(c4.y, p4.y), kM), 0x01010101u, m);
-            m = __dp4a(bytes_ge(__vabsdiffu4(c4.z, p4.z), kM), 0x01010101u, m);
-            m = __dp4a(bytes_ge(__vabsdiffu4(c4.w, p4.w), kM), 0x01010101u, m);
-          }
+        for (int i = 0; i < 4; ++i) {
+          if (i == 3 && !mv_row3) break;
+          const uint4 c4 = *reinterpret_cast<const uint4*>(cur + mv_toff + i * 8 * kMmTW);
+          const uint4 p4 = *reinterpret_cast<const uint4*>(prv + mv_toff + i * 8 * kMmTW);
+          m = __dp4a(bytes_ge(__vabsdiffu4(c4.x, p4.x), kM), 0x01010101u, m);
+          m = __dp4a(bytes_ge(__vabsdiffu4(c4.y, p4.y), kM), 0x01010101u, m);
+          m = __dp4a(bytes_ge(__vabsdiffu4(c4.z, p4.z), kM), 0x01010101u, m);
+          m = __dp4a(bytes_ge(__vabsdiffu4(c4.w, p4.w), kM), 0x01010101u, m);
         }
-        return (cM0 >> 7) | ((cM1 >> 7) << 16);               // <= 32 hits per half and lane
+        return (m >> 7) << mv_shift;                           // <= 64 hits per lane, in the half of its field
       };
       auto move_step = [&](int j, uint32_t (&pend)[NS]) {
         const uint32_t gl = gload + (uint32_t)j;
@@ -274,22 +279,28 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
         for (int s = 0; s < NS; ++s)
           pend[s] = move_tile(slots + st * kStageBytes + s * kMmSlot, slots + sp * kStageBytes + s * kMmSlot, kMS[s]);
       };
-      // thresholds of one accumulator (this thread's pixel column, 64 columns = 32 row pairs each of pos and neg)
-      auto comb_tile = [&](const uint32_t (&pos)[32], const uint32_t (&neg)[32], uint32_t tS, uint32_t tL, uint32_t& accS, uint32_t& accL) {
+      // thresholds of one accumulator (this thread's pixel column, 64 columns = 32 row pairs each of pos and neg).
+      // HSET2.BF writes 1.0 per hit; the hits are counted with HADD2 (FMA-heavy pipe: the ALU pipe, which carries the
+      // compares, is the one that saturates) -- exact, <= 32 per half.  One multiply by 2^-24 turns the fp16 counts into
+      // their integer bit patterns (k * 2^-24 is the subnormal with bits k): low half = even rows, high half = odd rows.
+      auto comb_tile = [&](const uint32_t (&pos)[32], const uint32_t (&neg)[32], uint32_t tS, uint32_t tL, uint32_t& cntS, uint32_t& cntL) {
         const __half2 thS = *reinterpret_cast<const __half2*>(&tS);
         const __half2 thL = *reinterpret_cast<const __half2*>(&tL);
+        __half2 aS[4], aL[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t mS[16], mL[16];
+        for (int c = 0; c < 4; ++c) { aS[c] = __float2half2_rn(0.0f); aL[c] = __float2half2_rn(0.0f); }
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const __half2 r = __habs2(__hsub2(*reinterpret_cast<const __half2*>(&pos[16 * h + q]), *reinterpret_cast<const __half2*>(&neg[16 * h + q])));
-            mS[q] = __hge2_mask(r, thS);
-            mL[q] = __hge2_mask(r, thL);
-          }
-          accS = accS - (mS[0] + mS[1]) - (mS[2] + mS[3] + mS[4]) - (mS[5] + mS[6] + mS[7]) - (mS[8] + mS[9] + mS[10]) - (mS[11] + mS[12] + mS[13]) - (mS[14] + mS[15]);
-          accL = accL - (mL[0] + mL[1]) - (mL[2] + mL[3] + mL[4]) - (mL[5] + mL[6] + mL[7]) - (mL[8] + mL[9] + mL[10]) - (mL[11] + mL[12] + mL[13]) - (mL[14] + mL[15]);
+        for (int q = 0; q < 32; ++q) {
+          const __half2 r = __habs2(__hsub2(*reinterpret_cast<const __half2*>(&pos[q]), *reinterpret_cast<const __half2*>(&neg[q])));
+          aS[q & 3] = __hadd2(aS[q & 3], __hge2(r, thS));
+          aL[q & 3] = __hadd2(aL[q & 3], __hge2(r, thL));
         }
+        const uint32_t one_ulp = 0x00010001u;                  // 2^-24 in both halves
+        const __half2 ulp = *reinterpret_cast<const __half2*>(&one_ulp);
+        const __half2 sS = __hmul2(__hadd2(__hadd2(aS[0], aS[1]), __hadd2(aS[2], aS[3])), ulp);
+        const __half2 sL = __hmul2(__hadd2(__hadd2(aL[0], aL[1]), __hadd2(aL[2], aL[3])), ulp);
+        cntS = *reinterpret_cast<const uint32_t*>(&sS);
+        cntL = *reinterpret_cast<const uint32_t*>(&sL);
       };
 
       {                                                      // L_0: the frame before the first one of this item
@@ -330,24 +341,20 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
         if (lane == 0) mbar_arrive(&free_bar);               // accumulators and the stage of load k-1 may be overwritten
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-          uint32_t accS = 0u, accL = 0u;                     // pair-coded: low half = even rows (top field), high = odd rows
-          comb_tile(pos[s], neg[s], tSS[s], tLS[s], accS, accL);
-          // warp totals; decode of the pair code: low half = hits in even rows, high half = (odd - even) mod 2^16
-          const uint32_t rS = __reduce_add_sync(0xFFFFFFFFu, accS), rL = __reduce_add_sync(0xFFFFFFFFu, accL);
+          uint32_t cntS, cntL;                               // low half = hits in even rows (top field), high half = odd rows
+          comb_tile(pos[s], neg[s], tSS[s], tLS[s], cntS, cntL);
+          const uint32_t rS = __reduce_add_sync(0xFFFFFFFFu, cntS), rL = __reduce_add_sync(0xFFFFFFFFu, cntL);   // <= 32 x 32 per half
           const uint32_t rM = __reduce_add_sync(0xFFFFFFFFu, pendM[s]);
-          // counts[] layout of one class: [field][move, shima, lshima]; lane i < 6 publishes counter i
-          const uint32_t src = (lane == 0 || lane == 3) ? rM : ((lane == 1 || lane == 4) ? rS : rL);
-          uint32_t v = lane < 3 ? (src & 0xFFFFu) : ((lane == 3 ? (src >> 16) : ((src >> 16) + src)) & 0xFFFFu);
+          uint32_t v = (((rM & pub_selM) | (rS & pub_selS) | (rL & pub_selL)) >> pub_shift) & 0xFFFFu;
           if (any_fix) {
-            // lanes spread the 8-bit fields over 4 words of 32 lanes: sums stay < 256 per field only if <= 7 hits per lane
+            // <= 4 excluded rows per lane -> <= 4 hits per 8-bit field and lane, x 32 lanes = 128 < 256
             const uint32_t fS = __reduce_add_sync(0xFFFFFFFFu, fixv[s] & 0xFFFFu), fL = __reduce_add_sync(0xFFFFFFFFu, fixv[s] >> 16);
-            // per lane <= 4 excluded rows -> <= 4 hits per 8-bit field... x 32 lanes = 128 < 256
             if (lane == 1) v -= fS & 0xFFu;
             if (lane == 4) v -= (fS >> 8) & 0xFFu;
             if (lane == 2) v -= fL & 0xFFu;
             if (lane == 5) v -= (fL >> 8) & 0xFFu;
           }
-          if (lane < 6 && v) atomicAdd(&red[k & 3][s * 8 + lane], v);
+          if (lane < 6 && v) atomicAdd(pub_red + ((k & 3) * 16 + s * 8), v);
         }
         if (k < nf) move_step(k + 1, pendM);
       }
