@@ -605,6 +605,16 @@ static int launch_comb_mma(amtk_ctx* ctx, const amtk_clip* clip, const Window& w
   AMTK_CUDA(cudaGetLastError());
   if (ctx->timing) { AMTK_CUDA(cudaEventRecord(ev.second, ctx->stream)); ctx->timing_events.push_back(ev); }
   ctx->launches += 1;
+  // experimental kernel: read its watchdog record back (costs a stream synchronisation per launch)
+  int dbg[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  AMTK_CUDA(cudaMemcpyAsync(dbg, args.queue + 16, sizeof(dbg), cudaMemcpyDeviceToHost, ctx->stream));
+  AMTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (dbg[0]) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "comb_mma<%d>: a device-side wait timed out (wait %d, step %d, CTA %d, thread %d, parity %d); results discarded",
+             NS, dbg[1], dbg[2], dbg[3], dbg[4], dbg[5]);
+    AMTK_FAIL(msg);
+  }
   return 1;
 }
 

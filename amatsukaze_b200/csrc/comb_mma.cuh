@@ -19,8 +19,9 @@
 // the two fields, so one pair-coded accumulator carries both field counters.  The inter-frame difference stays on the
 // SIMT side (VABSDIFF4 + SWAR compare + IDP.4A on the raw bytes of the current and the previous slot).
 //
-// Same integer spec, same counters, bit-identical results (integer adds commute).  One CTA (4 warps) = one tile stream;
-// 4 CTAs per SM (4 x 128 tensor-memory columns = all 512).
+// Same integer spec, same counters, bit-identical results (integer adds commute).  Measured SLOWER than the warp-stream
+// kernel (1.5 ms vs 1.23 ms per 1800 1080p frames): it is an opt-in experiment (AMTK_COMB_MMA=1|2), not the
+// product path.  Every device-side wait has a watchdog (mm_wait): a protocol error fails the call, it cannot hang the GPU.
 #pragma once
 #include <cuda_fp16.h>
 #include "amtk_internal.h"
@@ -71,6 +72,42 @@ __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {        // one 32-bi
   uint32_t v;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
   return v;
+}
+
+// Watchdog wait.  The kernel is an experiment with a known rare hang (see the header of this file / DESIGN.md 3.1b), so no
+// wait may spin forever: after ~1 s a thread records (code, step, CTA, thread) in dbg[] and raises dbg[0]; from then on
+// every wait of every CTA returns at once, the launch drains with garbage results and the host reports the failure.
+constexpr long long kMmWaitLimit = 2000000000ll;           // clock64 ticks (~1 s)
+__device__ __noinline__ void mm_wait_slow(uint64_t* bar, uint32_t parity, int* dbg, int code, int step, bool sleepy) {
+  const long long t0 = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return;
+    if (sleepy) __nanosleep(64);
+    if ((spin & 15u) == 15u) {
+      if (*reinterpret_cast<volatile int*>(dbg)) return;
+      if (clock64() - t0 > kMmWaitLimit) {
+        if (atomicCAS(dbg, 0, 1) == 0) { dbg[1] = code; dbg[2] = step; dbg[3] = (int)blockIdx.x; dbg[4] = (int)threadIdx.x; dbg[5] = (int)parity; __threadfence(); }
+        return;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void mm_wait(uint64_t* bar, uint32_t parity, int* dbg, int code, int step, bool sleepy = false) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  if (!done) mm_wait_slow(bar, parity, dbg, code, step, sleepy);
 }
 
 // shared-memory matrix descriptor (sm_100 format: version 1 at bit 46)
@@ -135,6 +172,7 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  int* const dbg = a.queue + 16;                             // watchdog record (64 bytes after the queue counter, zeroed per launch)
   const uint32_t tmem_base = tmem_holder;
   const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 lanes
   const uint32_t slots_u32 = smem_u32(slots);
@@ -158,9 +196,23 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
   uint32_t gload = 0;          // stage loads consumed so far (ring position)
   uint32_t nmma = 0;           // MMA batches committed so far (phase of mma_bar)
   uint32_t nfree = 0;          // completed phases of free_bar (producer)
+  int* pend_crow = nullptr;    // producer: counters of the last frame of the previous item still sit in red[]
+  int pend_k = 0;
   for (;;) {
     if (tid == kMmConsumerWarps * 32) item_s = atomicAdd(a.queue, 1);
     __syncthreads();
+    // Every consumer has published the last frame of the previous item before it reached this barrier: flush it now.
+    // (A closing arrival on free_bar instead would let the consumers complete TWO phases -- last step, closing -- without
+    // the producer in between; a parity wait that is two phases late never returns.  That was the rare hang of the first
+    // version: watchdog record "wait 2, step nf, producer".)
+    if (producer && pend_k > 0) {
+      if (lane < 8 * NS) {
+        const uint32_t v = red[pend_k & 3][lane];
+        red[pend_k & 3][lane] = 0u;
+        if (pend_crow && v) atomicAdd(pend_crow + (size_t)pend_k * 12, (int)v);
+      }
+      pend_k = 0;
+    }
     // warp-uniform by construction; the reduction tells the compiler so (uniform registers for all the bookkeeping)
     const int pair = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)item_s);
     if (NS * pair >= a.nitems) break;
@@ -201,7 +253,7 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
       auto issue_mma = [&](int j) {                          // all lanes wait for the stage, lane 0 issues
         const uint32_t gl = gload + (uint32_t)j;
         const int st = (int)(gl & (kMmStages - 1));
-        mbar_wait(&full_bar[st], (gl / kMmStages) & 1u);
+        mm_wait(&full_bar[st], (gl / kMmStages) & 1u, dbg, 1, j);
         if (lane == 0) {
           tc_fence_after();
 #pragma unroll
@@ -231,13 +283,12 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
       __syncwarp();
       issue_mma(1);
       for (int k = 1; k <= nf; ++k) {
-        mbar_wait_sleep(&free_bar, nfree & 1u); ++nfree;     // accumulators of step k are in registers; stage of load k-1 is free
+        mm_wait(&free_bar, nfree & 1u, dbg, 2, k, true); ++nfree;   // accumulators of step k are in registers; stage of load k-1 is free
         if (lane == 0 && (k + kMmStages - 1) < nloads) issue_load(k + kMmStages - 1);
         if (k < nf) issue_mma(k + 1);
         if (k > 1) flush(k - 1);                             // every consumer published frame k-1 before it arrived for step k
       }
-      mbar_wait_sleep(&free_bar, nfree & 1u); ++nfree;       // the consumers' closing arrival: frame nf is published
-      flush(nf);
+      pend_crow = crow; pend_k = nf;                         // frame nf is flushed after the next block barrier
       nmma += (uint32_t)nf;
     } else {
       // =========================== consumer warps ===========================
@@ -274,7 +325,7 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
       auto move_step = [&](int j, uint32_t (&pend)[NS]) {
         const uint32_t gl = gload + (uint32_t)j;
         const int st = (int)(gl & (kMmStages - 1)), sp = (int)((gl - 1) & (kMmStages - 1));
-        mbar_wait(&full_bar[st], (gl / kMmStages) & 1u);
+        mm_wait(&full_bar[st], (gl / kMmStages) & 1u, dbg, 4, j);
 #pragma unroll
         for (int s = 0; s < NS; ++s)
           pend[s] = move_tile(slots + st * kStageBytes + s * kMmSlot, slots + sp * kStageBytes + s * kMmSlot, kMS[s]);
@@ -305,12 +356,12 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
 
       {                                                      // L_0: the frame before the first one of this item
         const int st = (int)(gload & (kMmStages - 1));
-        mbar_wait(&full_bar[st], (gload / kMmStages) & 1u);
+        mm_wait(&full_bar[st], (gload / kMmStages) & 1u, dbg, 5, 0);
       }
       uint32_t pendM[NS];
       move_step(1, pendM);
       for (int k = 1; k <= nf; ++k) {
-        mbar_wait(&mma_bar, nmma & 1u); ++nmma;              // both accumulators of step k are complete
+        mm_wait(&mma_bar, nmma & 1u, dbg, 6, k); ++nmma;       // both accumulators of step k are complete
         tc_fence_after();
         uint32_t pos[NS][32], neg[NS][32];
 #pragma unroll
@@ -358,8 +409,6 @@ __global__ void __launch_bounds__(kMmThreads, 4 / NS) comb_mma_kernel(const __gr
         }
         if (k < nf) move_step(k + 1, pendM);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&free_bar);                 // closing arrival: the counters of frame nf are published
     }
     gload += (uint32_t)nloads;
   }

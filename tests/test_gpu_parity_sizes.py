@@ -282,17 +282,13 @@ def test_fused_step_with_coresident_logo_kernel(oracle, monkeypatch, mode):
         c.close()
 
 
-_MMA = pytest.mark.skipif(not __import__("os").environ.get("AMTK_TEST_MMA"),
-                          reason="experimental tensor-core kernels: opt in with AMTK_TEST_MMA=1 (the one-tile form has hung "
-                                 "about once in 50 launches, DESIGN.md section 3.1b)")
-
-
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("variant", ["ws", "cta_ring", pytest.param("mma1", marks=_MMA), pytest.param("mma2", marks=_MMA)])
+@pytest.mark.parametrize("variant", ["ws", "cta_ring", "mma1", "mma2"])
 def test_every_comb_kernel_variant_is_bit_exact(oracle, monkeypatch, variant):
     """The streaming pass exists in four forms: the default warp-stream kernel (comb_stream.cuh), the round-1 CTA-ring kernel
     (comb_kernels.cuh, AMTK_COMB_WS=0) and the two tensor-core forms (comb_mma.cuh: stencil as tcgen05.mma.kind::i8 with the
-    TMA-staged tile as the MN-major operand; AMTK_COMB_MMA=1: one tile per CTA step, =2: two).  All must return the spec
+    TMA-staged tile as the MN-major operand; AMTK_COMB_MMA=1: one tile per CTA step, =2: two; every device-side wait of
+    that kernel has a watchdog, so a protocol error fails the call instead of hanging the GPU).  All must return the spec
     oracle's counters bit for bit: ragged shapes (partial tile columns and rows, planes smaller than a tile, odd tile
     counts -> filler stream), extreme thresholds, edge rows, frame-range calls with a halo frame, and configs[1]/[2]
     geometry."""
