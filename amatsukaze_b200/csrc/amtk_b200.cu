@@ -1448,44 +1448,65 @@ int amtk_scan_logo(amtk_ctx* ctx, const amtk_clip* clip, int service_id, const c
   if (!validate_clip(clip, true)) return 0;
   if (clip->bytes_per_sample != 1) AMTK_FAIL("LogoScan supports 8-bit clips only (as the reference, LogoScan.hpp:812)");
   const int n = clip->num_frames;
-  // ---- MakeInitialLogo (:917-921): every frame is offered until max_frames valid ones were gathered ----
+  // ---- MakeInitialLogo (:917-921): frames are offered in reading order until max_frames valid ones were gathered (:884);
+  //      every 200 frames read the callback gets (position/size * 50, readCount, 0, numFrames) and may cancel (:905-910).
+  //      The clip replaces the decoder, so "position / file size" is frames read / frames in the clip. ----
   std::vector<uint8_t> valid((size_t)n), select((size_t)n, 0);
-  {
-    ScanGuard probe;                       // pass 1: validity of every frame
-    if (!amtk_scan_create(ctx, w, h, clip->log_uvx, clip->log_uvy, thy, &probe.s)) return 0;
-    if (!amtk_scan_add_frames(probe.s, clip, imgx, imgy, 0, n, nullptr, valid.data())) return 0;
-  }
   int numFrames = 0, nread = 0;
-  for (int i = 0; i < n && numFrames < max_frames; ++i) { ++nread; if (valid[i]) { select[i] = 1; ++numFrames; } }
-  if (cb && !cb(50.0f * nread / std::max(1, n), nread, 0, numFrames)) AMTK_FAIL("Cancel requested");
+  {
+    ScanGuard probe;                       // validity only; the accumulation proper runs once the cut-off frame is known
+    if (!amtk_scan_create(ctx, w, h, clip->log_uvx, clip->log_uvy, thy, &probe.s)) return 0;
+    while (nread < n && numFrames < max_frames) {
+      const int blk = std::min(200, n - nread);
+      if (!amtk_scan_add_frames(probe.s, clip, imgx, imgy, nread, blk, nullptr, valid.data() + nread)) return 0;
+      int i = nread;
+      for (; i < nread + blk && numFrames < max_frames; ++i) if (valid[i]) { select[i] = 1; ++numFrames; }
+      // the frame on which the limit is reached is the last one processed (onFrame returns false on the NEXT call, :884)
+      nread = (numFrames >= max_frames) ? i : nread + blk;
+      if ((nread % 200) == 0 && cb && !cb(50.0f * (float)nread / (float)std::max(1, n), nread, 0, numFrames)) AMTK_FAIL("Cancel requested");
+    }
+  }
   const size_t ndata = ((size_t)w * h + 2 * (size_t)(w >> clip->log_uvx) * (h >> clip->log_uvy)) * 2;
   std::vector<float> logodata(ndata);
   {
     ScanGuard init;
     if (!amtk_scan_create(ctx, w, h, clip->log_uvx, clip->log_uvy, thy, &init.s)) return 0;
-    if (!amtk_scan_add_frames(init.s, clip, imgx, imgy, 0, n, select.data(), nullptr)) return 0;
+    if (!amtk_scan_add_frames(init.s, clip, imgx, imgy, 0, nread, select.data(), nullptr)) return 0;
     if (!amtk_scan_get_logo(init.s, 255, 0, logodata.data())) return 0;      // "Insufficient logo frames"
   }
-  // ---- ReMakeLogo x2 (:923-1036) ----
+  // ---- ReMakeLogo x2 (:923-1036): 20-fade sweep over the STORED frames; every 100 of them the callback gets
+  //      (i / numFrames * 25 + progressbase, i, numFrames, numFrames) (:977-982); frames whose best fade index is > 8 are
+  //      accumulated again (:1018-1021).  Only frames [0, nread) are touched. ----
   float fades[20];
   for (int fi = 0; fi < 20; ++fi) fades[fi] = 0.1f * fi;                      // :967
-  std::vector<float> sweep((size_t)n * 20);
+  const int kBlock = 128;                                                      // clip frames per sweep call
+  std::vector<float> sweep((size_t)kBlock * 20);
   for (int round = 0; round < 2; ++round) {
+    const float progressbase = 50.0f + 25.0f * round;                          // :1064-1068
     LogoGuard raw, deint;
     if (!amtk_logo_create(ctx, logodata.data(), w, h, clip->log_uvx, clip->log_uvy, w, h, imgx, imgy, &raw.l)) return 0;
     if (!amtk_logo_deint(raw.l, &deint.l) || !amtk_logo_create_mask(deint.l, 0.1f)) return 0;      // :929-931
-    if (!amtk_logo_eval_fades(ctx, clip, deint.l, fades, 20, 0, n, sweep.data(), 0)) return 0;
     std::vector<uint8_t> sel2((size_t)n, 0);
-    for (int i = 0; i < n; ++i) {
-      if (!select[i]) continue;
-      float best = FLT_MAX; int bi = 0;                                        // :964-975, first strict minimum of |score|
-      for (int fi = 0; fi < 20; ++fi) { const float r = std::fabs(sweep[(size_t)i * 20 + fi]); if (r < best) { best = r; bi = fi; } }
-      sel2[i] = bi > 8;                                                         // :1018-1021
+    int stored = 0;                                                            // the reference's i: index among the stored frames
+    for (int f0 = 0; f0 < nread; f0 += kBlock) {
+      const int blk = std::min(kBlock, nread - f0);
+      bool any = false;
+      for (int i = f0; i < f0 + blk; ++i) any = any || select[i];
+      if (!any) continue;
+      if (!amtk_logo_eval_fades(ctx, clip, deint.l, fades, 20, f0, blk, sweep.data(), 0)) return 0;
+      for (int i = f0; i < f0 + blk; ++i) {
+        if (!select[i]) continue;
+        float best = FLT_MAX; int bi = 0;                                      // :964-975, first strict minimum of |score|
+        for (int fi = 0; fi < 20; ++fi) { const float r = std::fabs(sweep[(size_t)(i - f0) * 20 + fi]); if (r < best) { best = r; bi = fi; } }
+        sel2[i] = bi > 8;                                                      // :1018-1021
+        if ((stored % 100) == 0 && cb && !cb((float)stored / (float)numFrames * 25.0f + progressbase, stored, numFrames, numFrames))
+          AMTK_FAIL("Cancel requested");
+        ++stored;
+      }
     }
-    if (cb && !cb(50.0f + 25.0f * (round + 1) - 0.01f, n, numFrames, numFrames)) AMTK_FAIL("Cancel requested");
     ScanGuard acc;
     if (!amtk_scan_create(ctx, w, h, clip->log_uvx, clip->log_uvy, thy, &acc.s)) return 0;
-    if (!amtk_scan_add_frames(acc.s, clip, imgx, imgy, 0, n, sel2.data(), nullptr)) return 0;
+    if (!amtk_scan_add_frames(acc.s, clip, imgx, imgy, 0, nread, sel2.data(), nullptr)) return 0;
     if (!amtk_scan_get_logo(acc.s, 255, 1, logodata.data())) return 0;        // :1030-1035
   }
   if (cb && !cb(1.0f, numFrames, numFrames, numFrames)) AMTK_FAIL("Cancel requested");     // :1071-1073

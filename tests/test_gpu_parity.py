@@ -348,7 +348,9 @@ def test_scan_logo_pipeline(ctx, oracle, tmp_path):
     dst = str(tmp_path / "gen.lgd")
     calls = []
     ctx.scan_logo(clip, dst, sx, sy, sw, sh, thy, maxf, service_id=410, cb=lambda p, a, b, c: calls.append((p, a, b, c)) or True)
-    assert calls and calls[-1][0] == 1.0
+    # callback contract of the reference (LogoScan.hpp:905-910,977-982,1071): every 200 frames read in MakeInitialLogo (none
+    # here: the limit is hit after < 200 frames), every 100 stored frames in each ReMakeLogo (i = 0 only), then (1, n, n, n)
+    assert calls == [(50.0, 0, maxf, maxf), (75.0, 0, maxf, maxf), (1.0, maxf, maxf, maxf)], calls
     got = ab.Logo.load(dst)
     gi = got.info()
     assert (gi.w, gi.h, gi.imgw, gi.imgh, gi.imgx, gi.imgy) == (sw, sh, w, h, sx, sy)
@@ -381,6 +383,29 @@ def test_scan_logo_pipeline(ctx, oracle, tmp_path):
         data = sc2.get_logo(255, True)
         assert data is not None
     assert np.array_equal(got.tables()["data"].view(np.uint32), data.view(np.uint32))
+    # a longer clip: the 200-frame and 100-frame callback cadences, progress formulas and a cancel in the MIDDLE of a pass
+    n2 = 450
+    fr2 = synth.make_frames(0, n2, w, h, seed=0x5EED0005, device="cuda", mode="flat", logo=lg, imgx=sx, imgy=sy)
+    clip2 = _clip(fr2, w, h)
+    calls2 = []
+    ctx.scan_logo(clip2, dst, sx, sy, sw, sh, thy, 100000, cb=lambda p, a, b, c: calls2.append((p, a, b, c)) or True)
+    Y2, U2, V2 = synth.split_planes(fr2, w, h)
+    sc3 = po.OracleScan(sw, sh, thy)
+    nv = [0]
+    for i in range(n2):
+        nv.append(nv[-1] + (1 if sc3.add_frame(Y2[i][sy:sy + sh, sx:sx + sw], U2[i][sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2],
+                                               V2[i][sy // 2:(sy + sh) // 2, sx // 2:(sx + sw) // 2]) else 0))
+    nvalid = nv[-1]
+    assert nvalid > 200
+    want = [(np.float32(50.0 * r / n2), r, 0, nv[r]) for r in (200, 400)]
+    for base in (50.0, 75.0):
+        want += [(np.float32(np.float32(i) / np.float32(nvalid) * np.float32(25.0) + np.float32(base)), i, nvalid, nvalid) for i in range(0, nvalid, 100)]
+    want.append((1.0, nvalid, nvalid, nvalid))
+    assert [(np.float32(c[0]),) + c[1:] for c in calls2] == [(np.float32(x[0]),) + x[1:] for x in want], (calls2, want)
+    seen = []
+    with pytest.raises(ab.AmtkError, match="Cancel requested"):
+        ctx.scan_logo(clip2, dst, sx, sy, sw, sh, thy, 100000, cb=lambda p, a, b, c: seen.append(a) or len(seen) < 5)
+    assert len(seen) == 5                                    # stopped inside the first ReMakeLogo, not after it
     # cancel + insufficient frames behave like the reference
     with pytest.raises(ab.AmtkError, match="Cancel requested"):
         ctx.scan_logo(clip, dst, sx, sy, sw, sh, thy, maxf, cb=lambda *a: False)
