@@ -363,11 +363,13 @@ static int pick_comb_R(int hY, int hC) {
 }
 
 // ---- round-2 streaming kernel (comb_stream.cuh): independent warp streams, 8-bit samples ----------------------
-struct WsVariant { int R, stages, warps, TH, boxH, smem; void (*kernel)(const WsArgs); };
-template <typename Cfg> static WsVariant make_ws() { return WsVariant{ Cfg::R, Cfg::STAGES, Cfg::WARPS, Cfg::TH, Cfg::BOXH, Cfg::SMEM, comb_ws_kernel<Cfg> }; }
+struct WsVariant { int R, stages, warps, bps, TH, boxH, smem; void (*kernel)(const WsArgs); };
+template <typename Cfg> static WsVariant make_ws() { return WsVariant{ Cfg::R, Cfg::STAGES, Cfg::WARPS, Cfg::BPS, Cfg::TH, Cfg::BOXH, Cfg::SMEM, comb_ws_kernel<Cfg> }; }
 static const WsVariant* ws_variants(int* n) {
   static const WsVariant v[] = { make_ws<WsCfg<17, 2>>(), make_ws<WsCfg<15, 2>>(), make_ws<WsCfg<16, 2>>(), make_ws<WsCfg<9, 2>>(), make_ws<WsCfg<15, 3>>(), make_ws<WsCfg<12, 2>>(), make_ws<WsCfg<10, 2>>(),
-                                 make_ws<WsCfg<15, 2, 7>>(), make_ws<WsCfg<13, 2, 5>>(), make_ws<WsCfg<15, 2, 2>>(), make_ws<WsCfg<15, 3, 3>>() };
+                                 make_ws<WsCfg<15, 2, 7>>(), make_ws<WsCfg<13, 2, 5>>(), make_ws<WsCfg<15, 2, 2>>(), make_ws<WsCfg<15, 3, 3>>(),
+                                 // 16-bit containers with <= 10 significant bits (YUV420P10): integer-lane stencil, no conversion
+                                 make_ws<WsCfg<15, 2, 4, 2>>(), make_ws<WsCfg<16, 2, 4, 2>>(), make_ws<WsCfg<17, 2, 4, 2>>() };
   *n = (int)(sizeof(v) / sizeof(v[0]));
   return v;
 }
@@ -388,7 +390,8 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   const int wY = clip->width, wC = clip->width >> clip->log_uvx;
   const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_ws_R(hY, hC);
   int nvar = 0; const WsVariant* vars = ws_variants(&nvar); const WsVariant* V = nullptr;
-  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].stages == ctx->knobs.comb_ws_stages && vars[i].warps == ctx->knobs.comb_ws_warps) V = &vars[i];
+  const int bps = clip->bytes_per_sample;
+  for (int i = 0; i < nvar; ++i) if (vars[i].R == R && vars[i].stages == ctx->knobs.comb_ws_stages && vars[i].warps == ctx->knobs.comb_ws_warps && vars[i].bps == bps) V = &vars[i];
   if (!V) AMTK_FAIL("comb: no warp-stream kernel variant for the requested AMTK_COMB_* settings");
   const int WW = V->warps;
   WsArgs args;
@@ -397,7 +400,7 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
                                        ctx->knobs.comb_l2 == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   for (int pl = 0; pl < 3; ++pl) {
     const long long off = pl == 0 ? 0 : (pl == 1 ? clip->off_u : clip->off_v);
-    cuuint64_t gdim[3] = { (cuuint64_t)(pl ? wC : wY), (cuuint64_t)(pl ? hC : hY), (cuuint64_t)win.count };
+    cuuint64_t gdim[3] = { (cuuint64_t)(pl ? wC : wY) * bps, (cuuint64_t)(pl ? hC : hY), (cuuint64_t)win.count };     // x in BYTES (u8 element type also for 16-bit containers)
     cuuint64_t gstr[2] = { (cuuint64_t)(pl ? clip->pitch_uv : clip->pitch_y), (cuuint64_t)clip->frame_stride };
     cuuint32_t box[3] = { (cuuint32_t)kWsTW, (cuuint32_t)V->boxH, 1u };
     cuuint32_t estr[3] = { 1u, 1u, 1u };
@@ -406,11 +409,11 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
       AMTK_FAIL("cuTensorMapEncodeTiled failed");
   }
   // chroma remainder columns of at most 64 bytes: U and V side by side in one tile through a 4-D map (x, plane, y, frame)
-  const int remC = wC % kWsTW;
+  const int remC = (wC * bps) % kWsTW;
   const long long uv_dist = clip->off_v - clip->off_u;
   const bool pair_uv = ctx->knobs.comb_merge_uv && remC > 0 && remC <= kWsTW / 2 && uv_dist > 0 && (uv_dist & 15) == 0;
   if (pair_uv) {
-    cuuint64_t gdim[4] = { (cuuint64_t)wC, 2u, (cuuint64_t)hC, (cuuint64_t)win.count };
+    cuuint64_t gdim[4] = { (cuuint64_t)wC * bps, 2u, (cuuint64_t)hC, (cuuint64_t)win.count };
     cuuint64_t gstr[3] = { (cuuint64_t)uv_dist, (cuuint64_t)clip->pitch_uv, (cuuint64_t)clip->frame_stride };
     cuuint32_t box[4] = { (cuuint32_t)(kWsTW / 2), 2u, (cuuint32_t)V->boxH, 1u };
     cuuint32_t estr[4] = { 1u, 1u, 1u, 1u };
@@ -422,13 +425,20 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   int tile0 = 0, nc = 0;
   auto thresholds = [&](WsClass& C, bool chroma) {
     C.cls = chroma ? 1 : 0; C.H = chroma ? hC : hY;
-    C.thM = (unsigned)(0x80 - (chroma ? prm->th_move_c : prm->th_move_y)) * 0x01010101u;
-    C.thS = (unsigned)(chroma ? prm->th_shima_c : prm->th_shima_y) * 0x00010001u;     // integer k in [1,2047] IS the fp16 bit pattern of k*2^-24
-    C.thL = (unsigned)(chroma ? prm->th_lshima_c : prm->th_lshima_y) * 0x00010001u;
+    const int tM = chroma ? prm->th_move_c : prm->th_move_y, tS = chroma ? prm->th_shima_c : prm->th_shima_y, tL = chroma ? prm->th_lshima_c : prm->th_lshima_y;
+    if (bps == 1) {
+      C.thM = (unsigned)(0x80 - tM) * 0x01010101u;
+      C.thS = (unsigned)tS * 0x00010001u;     // integer k in [1,2047] IS the fp16 bit pattern of k*2^-24
+      C.thL = (unsigned)tL * 0x00010001u;
+    } else {                                   // <= 10-bit samples: |d| <= 1023, |r| <= 6138, r is compared as 8192 + |r| (bit patterns)
+      C.thM = (unsigned)std::min(tM, 2047) * 0x00010001u;
+      C.thS = (unsigned)(8192 + std::min(tS, 8191)) * 0x00010001u;
+      C.thL = (unsigned)(8192 + std::min(tL, 8191)) * 0x00010001u;
+    }
   };
   for (int pl = 0; pl < 3; ++pl) {                         // 128-byte tiles of Y, U, V
     WsClass& C = args.cl[nc];
-    const int w = pl ? wC : wY;
+    const int w = (pl ? wC : wY) * bps;                    // bytes
     C.kind = 0; C.map = pl; thresholds(C, pl != 0);
     C.tilesX = (pl && pair_uv) ? w / kWsTW : (w + kWsTW - 1) / kWsTW;
     C.tile0 = tile0; C.ntiles = C.tilesX * (pl ? tyC : tyY);
@@ -437,7 +447,7 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   }
   if (pair_uv) {
     WsClass& C = args.cl[nc];
-    C.kind = 1; C.x0 = wC - remC; C.tilesX = 1; thresholds(C, true);
+    C.kind = 1; C.x0 = wC * bps - remC; C.tilesX = 1; thresholds(C, true);
     C.tile0 = tile0; C.ntiles = tyC; tile0 += C.ntiles; ++nc;
   }
   args.nclasses = nc;
@@ -461,7 +471,7 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (total + WW - 1) / WW);
   const int f0 = lo - win.first;
   if (!(plan.valid && plan.wY == wY && plan.hY == hY && plan.wC == wC && plan.hC == hC && plan.nf == nf && plan.f0 == f0 &&
-        plan.R == V->R && plan.item == ctx->knobs.comb_item && plan.ctas == occ * WW)) {
+        plan.R == V->R + 100 * bps && plan.item == ctx->knobs.comb_item && plan.ctas == occ * WW)) {
     int big = ctx->knobs.comb_item > 0 ? ctx->knobs.comb_item : 64, small = std::max(4, big / 4);
     // each warp should see at least ~6 big items; shrink for short clips
     while (big > 8 && (long long)ntiles * (nf / big) < 6LL * nwarps) { big /= 2; small = std::max(4, big / 4); }
@@ -480,7 +490,7 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
     AMTK_CUDA(cudaMemcpyAsync(plan.dev, segs.data(), seg_bytes, cudaMemcpyHostToDevice, ctx->stream));
     AMTK_CUDA(cudaStreamSynchronize(ctx->stream));           // pageable source vector dies at the end of this scope
     plan.nitems = (int)segs.size();
-    plan.wY = wY; plan.hY = hY; plan.wC = wC; plan.hC = hC; plan.nf = nf; plan.f0 = f0; plan.R = V->R;
+    plan.wY = wY; plan.hY = hY; plan.wC = wC; plan.hC = hC; plan.nf = nf; plan.f0 = f0; plan.R = V->R + 100 * bps;
     plan.item = ctx->knobs.comb_item; plan.ctas = occ * WW; plan.valid = true;
   }
   AMTK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(plan.dev) + plan.q_off, 0, 256, ctx->stream));
@@ -652,7 +662,8 @@ static int launch_comb(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     return 1;
   }
   if (clip->bytes_per_sample == 1 && ctx->knobs.comb_mma) return launch_comb_mma(ctx, clip, win, lo, hi, prm, dcounts, out_row0);
-  if (clip->bytes_per_sample == 1 && ctx->knobs.comb_ws) return launch_comb_ws(ctx, clip, win, lo, hi, prm, dcounts, out_row0);
+  if (ctx->knobs.comb_ws && (clip->bytes_per_sample == 1 || (clip->bits_per_sample <= 10 && ctx->knobs.comb_ws10)))
+    return launch_comb_ws(ctx, clip, win, lo, hi, prm, dcounts, out_row0);
   const int hY = clip->height, hC = clip->height >> clip->log_uvy;
   const int R = ctx->knobs.comb_R ? ctx->knobs.comb_R : pick_comb_R(hY, hC);
   int nvar = 0; const CombVariant* vars = comb_variants(&nvar); const CombVariant* V = nullptr;
@@ -841,6 +852,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_WS_STAGES")) c->knobs.comb_ws_stages = atoi(e);
   if (const char* e = getenv("AMTK_COMB_ITEM")) c->knobs.comb_item = atoi(e);
   if (const char* e = getenv("AMTK_COMB_MMA")) c->knobs.comb_mma = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_WS10")) c->knobs.comb_ws10 = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS_WARPS")) c->knobs.comb_ws_warps = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS_PF")) c->knobs.comb_ws_prefetch = atoi(e);
   cudaSetDevice(prev);

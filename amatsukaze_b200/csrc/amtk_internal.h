@@ -75,7 +75,8 @@ struct amtk_ctx {
     int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_sync = 0, comb_l2 = 64;
     int comb_item = 0;        // frames per long work item of the warp-stream kernel (0 = auto)
     int comb_ws_stages = 2;  // ring slots per warp stream
-    int comb_mma = 0;        // 1: tensor-core streaming kernel (comb_mma.cuh) for 8-bit clips
+    int comb_mma = 0;        // 1|2: tensor-core streaming kernel (comb_mma.cuh) for 8-bit clips, NS tiles per CTA step
+    int comb_ws10 = 1;       // 16-bit containers with <= 10 significant bits run the warp-stream kernel's integer-lane form
     int comb_ws_warps = 4;   // warp streams per CTA
     int comb_ws_prefetch = 0; // L2 prefetch distance of the warp streams' tile loads (steps ahead of the slot refill)
     int lite_ctas = 5;      // CTAs per SM of the small-footprint logo kernel when it runs on its own

@@ -33,9 +33,10 @@ constexpr int kWsTW = 128;               // tile width in bytes
 constexpr int kWsRuns = 4;               // runs per warp (8 lanes x 16 bytes per row)
 constexpr int kWsWarps = 4;              // default warp streams per CTA: one per SM sub-partition
 
-template <int R_, int STAGES_, int WARPS_ = kWsWarps>
+template <int R_, int STAGES_, int WARPS_ = kWsWarps, int BPS_ = 1>
 struct WsCfg {
   static constexpr int R = R_, STAGES = STAGES_, WARPS = WARPS_;
+  static constexpr int BPS = BPS_;                          // 1: 8-bit samples; 2: 16-bit containers holding <= 10 bits (YUV420P10)
   static constexpr int TH = kWsRuns * R;                    // output rows per tile
   static constexpr int BOXH = TH + 4;                       // + 2 halo rows above and below
   static constexpr int STAGE_BYTES = kWsTW * BOXH;
@@ -251,6 +252,77 @@ __device__ __forceinline__ WsCounts ws_rows_sp(const uint8_t* __restrict__ cur, 
 #ifndef AMTK_WS_SP
 #define AMTK_WS_SP 0
 #endif
+// ---- YUV420P10 (16-bit containers, samples < 1024) --------------------------------------------------------------------
+// A 10-bit sample in a 16-bit lane IS an exact fp16 bit pattern (k * 2^-24, k < 2048): no conversion at all.  The response
+// needs 13 bits, so the stencil runs as 32-bit integer ops on the two 16-bit lanes at once (no lane ever leaves [0, 65535]:
+// r' = r + 8192), |r| comes from one packed max (VIMNMX.U16x2 of r' and 16384 - r'), and the thresholds are HSET2 on the
+// bit patterns (positive fp16 patterns below 0x7C00 order like integers).  The inter-frame difference is HADD2 + HSET2 |d|
+// (|d| < 1024: exact).  16-byte strips = 8 pixels per lane-row; ~42 instructions per 8 pixels = 2.6 per BYTE (8-bit: 5.75).
+struct W4 { uint32_t v[4]; };
+__device__ __forceinline__ W4 w4(const uint4 r) { W4 x; x.v[0] = r.x; x.v[1] = r.y; x.v[2] = r.z; x.v[3] = r.w; return x; }
+constexpr uint32_t kWs10Bias = 8192u * 0x00010001u;
+
+__device__ __forceinline__ void ws_row_masks10(const W4& h0, const W4& h1, const W4& h2, const W4& h3, const W4& h4,
+                                               const __half2 thS, const __half2 thL, uint32_t& accS, uint32_t& accL) {
+  uint32_t mS[4], mL[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t t = h2.v[q] * 4u + h0.v[q];
+    t = t + h4.v[q] + kWs10Bias;
+    const uint32_t u = h1.v[q] + h3.v[q];
+    const uint32_t rp = t - 3u * u;                        // r + 8192 in both lanes
+    const uint32_t m = __vmaxu2(rp, 2u * kWs10Bias - rp);  // 8192 + |r|
+    const __half2 mh = *reinterpret_cast<const __half2*>(&m);
+    mS[q] = __hge2_mask(mh, thS);
+    mL[q] = __hge2_mask(mh, thL);
+  }
+  accS = accS - (mS[0] + mS[1]) - (mS[2] + mS[3]);
+  accL = accL - (mL[0] + mL[1]) - (mL[2] + mL[3]);
+}
+
+template <int R, int PITCH>
+__device__ __forceinline__ WsCounts ws_rows10(const uint8_t* __restrict__ cur, uint4 (&P)[R],
+                                              const uint32_t kM, const uint32_t thS_bits, const uint32_t thL_bits) {
+  const __half2 thS = *reinterpret_cast<const __half2*>(&thS_bits);
+  const __half2 thL = *reinterpret_cast<const __half2*>(&thL_bits);
+  const __half2 thM = *reinterpret_cast<const __half2*>(&kM);
+  WsCounts c = { { 0u, 0u }, { 0u, 0u }, { 0u, 0u } };
+  W4 h0 = w4(*reinterpret_cast<const uint4*>(cur));
+  W4 h1 = w4(*reinterpret_cast<const uint4*>(cur + PITCH));
+  W4 h2 = w4(*reinterpret_cast<const uint4*>(cur + 2 * PITCH));
+  W4 h3 = w4(*reinterpret_cast<const uint4*>(cur + 3 * PITCH));
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const W4 h4 = w4(*reinterpret_cast<const uint4*>(cur + (j + 4) * PITCH));
+    const W4 pv = w4(P[j]);
+    const int f = j & 1;
+    uint32_t mM[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      mM[q] = __hge2_mask(__habs2(__hsub2(*reinterpret_cast<const __half2*>(&h2.v[q]), *reinterpret_cast<const __half2*>(&pv.v[q]))), thM);
+    c.M[f] = c.M[f] - (mM[0] + mM[1]) - (mM[2] + mM[3]);
+    if (kWsReloadPrev) P[j] = lds128(cur + (j + 2) * PITCH); else P[j] = make_uint4(h2.v[0], h2.v[1], h2.v[2], h2.v[3]);
+    ws_row_masks10(h0, h1, h2, h3, h4, thS, thL, c.S[f], c.L[f]);
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+  }
+  return c;
+}
+
+template <int PITCH>
+__device__ __noinline__ void ws_fixup10(const uint8_t* cur, uint32_t rows, uint32_t mine, uint32_t thS_bits, uint32_t thL_bits, WsCounts& c) {
+  const __half2 thS = *reinterpret_cast<const __half2*>(&thS_bits);
+  const __half2 thL = *reinterpret_cast<const __half2*>(&thL_bits);
+  for (uint32_t m = rows; m; m &= m - 1) {
+    const int j = __ffs(m) - 1;
+    if (!((mine >> j) & 1u)) continue;
+    const uint8_t* p = cur + j * PITCH;
+    uint32_t dS = 0u, dL = 0u;
+    ws_row_masks10(w4(*reinterpret_cast<const uint4*>(p)), w4(*reinterpret_cast<const uint4*>(p + PITCH)), w4(*reinterpret_cast<const uint4*>(p + 2 * PITCH)),
+                   w4(*reinterpret_cast<const uint4*>(p + 3 * PITCH)), w4(*reinterpret_cast<const uint4*>(p + 4 * PITCH)), thS, thL, dS, dL);
+    c.S[j & 1] -= dS; c.L[j & 1] -= dL;
+  }
+}
+
 // Rows the spec excludes from the comb response but the plain body counted: y < 2, H-2 <= y < H (no full window) and
 // the phantom rows H, H+1 (zero-filled by TMA; their windows still see the last two real rows).  The affected lanes
 // re-evaluate exactly those rows and ADD the masks back (the body subtracted them).  Rare: edge tiles only, and then
@@ -357,9 +429,10 @@ __global__ void __launch_bounds__(32 * Cfg::WARPS, Cfg::MIN_CTAS) comb_ws_kernel
       if (++st == S) { st = 0; ph ^= 1u; }
       mbar_wait(&full_bar[st], ph);
       const uint8_t* cur = tiles + st * Cfg::STAGE_BYTES + lane_off;
-      WsCounts c = AMTK_WS_SP ? ws_rows_sp<R, kWsTW>(cur, P, kM, tS, tL) : ws_rows<R, kWsTW>(cur, P, kM, tS, tL);
+      WsCounts c = Cfg::BPS == 2 ? ws_rows10<R, kWsTW>(cur, P, kM, tS, tL)
+                                 : (AMTK_WS_SP ? ws_rows_sp<R, kWsTW>(cur, P, kM, tS, tL) : ws_rows<R, kWsTW>(cur, P, kM, tS, tL));
       if (fix_rows) {
-        ws_fixup<kWsTW>(cur, fix_rows, fix_mine, tS, tL, c);
+        if (Cfg::BPS == 2) ws_fixup10<kWsTW>(cur, fix_rows, fix_mine, tS, tL, c); else ws_fixup<kWsTW>(cur, fix_rows, fix_mine, tS, tL, c);
         __syncwarp();
       }
       // slot -> field: lanes whose run starts on an odd row swap their two slots
@@ -374,7 +447,7 @@ __global__ void __launch_bounds__(32 * Cfg::WARPS, Cfg::MIN_CTAS) comb_ws_kernel
       if (lane < 6) {                                        // lane = field*3 + metric = the counts[] layout of one class
         const int fld = lane >= 3, met = lane - 3 * fld;
         uint32_t v = met == 0 ? (fld ? rM1 : rM0) : met == 1 ? (fld ? rS1 : rS0) : (fld ? rL1 : rL0);
-        v = met == 0 ? (v >> 7) : (met == 2 && kWsLviaIdp) ? v / 510u : decode_pair(v);
+        v = (met == 0 && Cfg::BPS == 1) ? (v >> 7) : (met == 2 && kWsLviaIdp && Cfg::BPS == 1) ? v / 510u : decode_pair(v);
         if (v) atomicAdd(crow + (size_t)k * 12, (int)v);     // (an unconditional RED measured 3 % slower: hot counter lines)
       }
     }

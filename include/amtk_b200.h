@@ -86,7 +86,8 @@ typedef struct amtk_clip {
                              /* takes slower plain-load kernels with identical results                    */
   int32_t log_uvx, log_uvy;  /* chroma subsampling shifts (1,1 for YV12 / YUV420P10)               */
   int32_t bytes_per_sample;  /* 1 (YV12) or 2 (YUV420P10/P12/P16, little endian)                   */
-  int32_t bits_per_sample;   /* 8, 10, 12 or 16: maxv = (1<<bits)-1 (LogoScan.hpp:1130,1575)       */
+  int32_t bits_per_sample;   /* 8, 10, 12 or 16: maxv = (1<<bits)-1 (LogoScan.hpp:1130,1575); every sample must be
+                              * <= maxv (the 10-bit combing path relies on it, as the reference's 10-bit formats do) */
   int32_t num_frames;
   int32_t on_device;         /* 1: base is a device pointer on the context's device; 0: host pointer */
 } amtk_clip;

@@ -316,6 +316,25 @@ def test_every_comb_kernel_variant_is_bit_exact(oracle, monkeypatch, variant):
         p2.th_shima_y, p2.th_lshima_y = 1530, 1531
         out = c.comb_frames(ab.yv12_clip(fr, w, h, 2, True), p2).cpu().numpy()
         assert out[0, 1] + out[0, 4] == (h - 4) * w and out[0, 2] + out[0, 5] == 0 and out[:, 0].sum() == 0
+        # YUV420P10 (16-bit containers, 10 significant bits): "ws" = the warp-stream kernel's integer-lane form (default for
+        # <= 10 bits), "cta_ring" = the round-1 fp32 kernel; ragged shapes incl. the merged U|V remainder tile and tiny planes
+        p10 = ab.default_comb_params()
+        p10.th_move_y, p10.th_shima_y, p10.th_lshima_y = 80, 48, 3000
+        p10.th_move_c, p10.th_shima_c, p10.th_lshima_c = 200, 1, 6138
+        for (w, h, n) in ((224, 136, 7), (320, 150, 5), (96, 62, 3), (1920, 64, 2), (64, 1100, 2)):
+            f8 = synth.make_frames(2, n, w, h, device="cuda", mode="telecine")
+            f16 = (f8.to(torch.int32) * 4 + (f8.to(torch.int32) & 3)).to(torch.int16).contiguous()
+            f16[:, ::7] = 1023                                   # the largest legal sample, scattered
+            clip10 = ab.yv12_clip(f16, w, h, n, True, bits=10)
+            got = c.comb_frames(clip10, p10).cpu().numpy()
+            a16 = f16.cpu().numpy().view(np.uint16)
+            ysz, csz = w * h, (w // 2) * (h // 2)
+            ref = po.or_comb_clip(a16[:, :ysz].reshape(n, h, w), a16[:, ysz:ysz + csz].reshape(n, h // 2, w // 2),
+                                  a16[:, ysz + csz:].reshape(n, h // 2, w // 2), p10.as_list())
+            assert np.array_equal(got, ref), (variant, "p10", w, h, np.argwhere(got != ref)[:5])
+            if n > 4:
+                part = np.concatenate([c.comb_frames(clip10, p10, 0, 3).cpu().numpy(), c.comb_frames(clip10, p10, 3, n - 3).cpu().numpy()])
+                assert np.array_equal(part, ref), (variant, "p10 ranges", w, h)
         # BASELINE geometries with default thresholds, whole call and two range calls (halo frame)
         prm = ab.default_comb_params()
         for (w, h, n) in ((1920, 1080, 40), (1440, 1080, 18)):
