@@ -276,10 +276,13 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     const int lanes = std::max(1, std::min(n, (ctx->sm_count * ctx->knobs.eval_waves) / slices));
     dim3 grid(slices, lanes);
     const bool u16 = clip->bytes_per_sample == 2;
+    const bool w64 = hl.w == 64 && sp.roi_w == 64 && ctx->knobs.eval_cw;     // compile-time width variant
+    const bool wh64 = w64 && hl.h == 64 && sp.roi_h == 64;                   // ... and height (LogoFrame::ScanFrame on 64x64 logos)
 #define AMTK_LAUNCH_SCORES(T, P)                                                                              \
   do {                                                                                                        \
-    AMTK_CUDA(cudaFuncSetAttribute(logo_scores_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    logo_scores_kernel<T, P><<<grid, kEvalThreads, smem, ctx->stream>>>(job);                                 \
+    void (*kfn)(const EvalJob) = wh64 ? logo_scores_kernel<T, P, 64, 64> : w64 ? logo_scores_kernel<T, P, 64, 0> : logo_scores_kernel<T, P, 0, 0>; \
+    AMTK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    kfn<<<grid, kEvalThreads, smem, ctx->stream>>>(job);                                                      \
   } while (0)
     if (!u16) { if (pxt == 1) AMTK_LAUNCH_SCORES(uint8_t, 1); else if (pxt == 2) AMTK_LAUNCH_SCORES(uint8_t, 2); else AMTK_LAUNCH_SCORES(uint8_t, 3); }
     else      { if (pxt == 1) AMTK_LAUNCH_SCORES(uint16_t, 1); else if (pxt == 2) AMTK_LAUNCH_SCORES(uint16_t, 2); else AMTK_LAUNCH_SCORES(uint16_t, 3); }
@@ -853,6 +856,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_ITEM")) c->knobs.comb_item = atoi(e);
   if (const char* e = getenv("AMTK_COMB_MMA")) c->knobs.comb_mma = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS10")) c->knobs.comb_ws10 = atoi(e);
+  if (const char* e = getenv("AMTK_EVAL_CW")) c->knobs.eval_cw = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS_WARPS")) c->knobs.comb_ws_warps = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS_PF")) c->knobs.comb_ws_prefetch = atoi(e);
   cudaSetDevice(prev);

@@ -69,6 +69,7 @@ struct amtk_ctx {
   amtk_encode_tiled_fn encode_tiled = nullptr;
   struct Knobs {            // kernel-variant selection; read from AMTK_* environment variables at context creation
     int eval_waves = 1;     // logo_scores_kernel CTAs per SM
+    int eval_cw = 1;        // 1: 64-pixel-wide logos use the compile-time-width kernel variant
     int comb_generic = 0;   // 1: force the plain-load comb kernel
     int comb_merge_uv = 1;  // U|V remainder columns share one tile
     int comb_part = -1;     // partition: -1 auto, 0 equal-share, 1 lock-step

@@ -57,14 +57,19 @@ __host__ __device__ inline size_t logo_scores_smem_bytes(int roi_n, int npx, int
          128 + 2 * (((size_t)raw_bytes_one + 127) & ~(size_t)127);
 }
 
-template <typename pixel_t, int PXT>
+// CW > 0: logo width AND staged ROI width are the compile-time constant CW (the common 64-pixel logos): every 5x5 window
+// address becomes an immediate and the index walkers lose their divisions (about half of the kernel's instructions were
+// integer bookkeeping, profiles/r02h_logo_scores_kernel_ncu_full_summary.txt).  CW = 0: both widths at run time.
+template <typename pixel_t, int PXT, int CW = 0, int CH = 0>        // CH > 0: logo height AND ROI height known as well (loops unroll)
 __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __grid_constant__ EvalJob job) {
   extern __shared__ float smem_f[];
   __shared__ __align__(8) uint64_t roi_bar[2];
   const int tid = threadIdx.x;
   const LogoDev& lg = job.logo;
-  const int w = lg.w, npx = lg.w * lg.h;
-  const int roi_n = job.roi_w * job.roi_h;
+  const int w = CW ? CW : lg.w, npx = w * (CH ? CH : lg.h);
+  const int roi_w = CW ? CW : job.roi_w;
+  const int roi_h = CH ? CH : job.roi_h;
+  const int roi_n = roi_w * roi_h;
   float* src = smem_f + (job.ab_smem ? 2 * ((npx + 3) & ~3) : 0);
   const float* sA = job.ab_smem ? smem_f : lg.A;                         // large logos read A,B through L1 instead
   const float* sB = job.ab_smem ? smem_f + ((npx + 3) & ~3) : lg.B;
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __gr
   uint8_t* raw_base = reinterpret_cast<uint8_t*>(work + (size_t)(job.pair_fades ? 2 : 1) * ((npx + 8 + 3) & ~3));
   raw_base += (128u - (smem_u32(raw_base) & 127u)) & 127u;
   const int raw_pitch = job.roi_box_w;                                   // elements per staged ROI row
-  const uint32_t raw_bytes = (uint32_t)raw_pitch * job.roi_h * sizeof(pixel_t);
+  const uint32_t raw_bytes = (uint32_t)raw_pitch * roi_h * sizeof(pixel_t);
   const uint32_t raw_stride = (raw_bytes + 127u) & ~127u;
 
   // ---- one-time: logo planes to smem, adopt feature pixels, pull their taps into registers ----
@@ -98,8 +103,8 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __gr
     }
   }
   // per-thread walk over image indices i = tid, tid+512, ... without divisions: (x,y) advance by (dx,dy)
-  const int roi_dx = kEvalThreads % job.roi_w, roi_dy = kEvalThreads / job.roi_w;
-  const int roi_y0 = tid / job.roi_w, roi_x0 = tid - roi_y0 * job.roi_w;
+  const int roi_dx = kEvalThreads % roi_w, roi_dy = kEvalThreads / roi_w;
+  const int roi_y0 = tid / roi_w, roi_x0 = tid - roi_y0 * roi_w;
   const int lg_dx = kEvalThreads % w, lg_dy = kEvalThreads / w;
   const int lg_y0 = tid / w, lg_x0 = tid - lg_y0 * w;
 
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __gr
       int x = roi_x0, y = roi_y0;
       for (int i = tid; i < roi_n; i += kEvalThreads) {
         dst[x + y * raw_pitch] = roi[x + (long long)y * job.pitch];
-        x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
+        x += roi_dx; y += roi_dy; if (x >= roi_w) { x -= roi_w; ++y; }
       }
       __syncthreads();
       raw = dst;
@@ -140,14 +145,14 @@ __global__ void __launch_bounds__(kEvalThreads, 1) logo_scores_kernel(const __gr
       for (int i = tid; i < roi_n; i += kEvalThreads) {
         const pixel_t* rp = raw + x + y * raw_pitch;
         float v;
-        if (job.src_mode == 0 && y > 0 && y < job.roi_h - 1) {
+        if (job.src_mode == 0 && y > 0 && y < roi_h - 1) {
           const int a = rp[-raw_pitch], b = rp[0], c = rp[raw_pitch];
           v = (float)(a + 2 * b + c + 2) / 4.0f;       // exact: integer < 2^24, division by 4
         } else {
           v = (float)rp[0];
         }
         src[i] = v;
-        x += roi_dx; y += roi_dy; if (x >= job.roi_w) { x -= job.roi_w; ++y; }
+        x += roi_dx; y += roi_dy; if (x >= roi_w) { x -= roi_w; ++y; }
       }
     }
     __syncthreads();
