@@ -512,7 +512,6 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   args.prefetch = ctx->knobs.comb_ws_prefetch;
   if (ctx->want_side_mark) {                                // fused step: the logo kernels may be queued on the side stream from here on
     AMTK_CUDA(cudaEventRecord(ctx->ev_side, ctx->stream));
-    ctx->side_flag = args.queue + 33;
     ctx->want_side_mark = false;
   }
   V->kernel<<<grid, 32 * WW, V->smem, ctx->stream>>>(args);
@@ -843,12 +842,6 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
     else cudaGetLastError();
   });
   c->encode_tiled = g_encode;
-  {
-    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      c->stream_wait_value32 = reinterpret_cast<amtk_stream_wait_value32_fn>(fn);
-    else cudaGetLastError();
-  }
   // per-context tuning knobs (defaults are the measured best; env AMTK_* overrides them for tools/tune_comb.py)
   if (const char* e = getenv("AMTK_COMB_STRIP")) c->knobs.comb_strip = atoi(e);
   if (const char* e = getenv("AMTK_COMB_STAGES")) c->knobs.comb_stages = atoi(e);
@@ -1353,20 +1346,19 @@ int amtk_scan_comb_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const
           if (!launch_scan_lite(ctx, clip, w, lo, hi, lg0, ds_, nlogos, 0, frame0, true)) return 0;
           return cuda_ok(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0), "cudaStreamWaitEvent") ? 1 : 0;
         }
-        if (ctx->knobs.scan_overlap && clip->on_device && ctx->stream_wait_value32) {
-          // Default for resident clips: the logo kernels go to the side stream right behind the comb launch.  They need a whole
-          // SM each (512 threads x 128 registers), so none of their CTAs starts while a comb CTA is resident on that SM: the
-          // block scheduler packs them into the comb kernel's tail (its persistent CTAs run dry within one short work item of
-          // each other) instead of waiting for the last comb CTA.  No co-residency, no change to the arithmetic of either
-          // kernel.  So that no logo CTA can take an SM BEFORE the comb kernel is resident, the side stream waits (stream
-          // memory operation) for the word the comb CTAs raise once all of them have started.
-          ctx->want_side_mark = true; ctx->side_flag = nullptr;
+        if (ctx->knobs.scan_overlap && clip->on_device) {
+          // Opt-in (AMTK_SCAN_OVERLAP=1): the logo kernels go to the side stream right behind the comb launch.  They need a
+          // whole SM each (512 threads x 128 registers), so they never share an SM with a comb CTA; the block scheduler packs
+          // them into the gaps at both ends of the comb kernel.  Measured: step 1.307 ms instead of 1.328 ms, but some logo
+          // CTAs take their SM BEFORE the comb kernel's CTAs arrive, which stretches the comb kernel's own duration by 60 us and
+          // would misstate its roofline fraction; gating the side stream on an "all comb CTAs resident" word (stream memory
+          // operation) kept the comb duration but cost the kernel as much as the overlap gained.  Default: serial.
+          ctx->want_side_mark = true;
           if (!launch_comb(ctx, clip, w, lo, hi, prm, dc, frame0)) { ctx->want_side_mark = false; return 0; }
+          const bool marked = !ctx->want_side_mark;            // the warp-stream launch recorded ev_side right before its kernel
           ctx->want_side_mark = false;
-          if (ctx->side_flag) {                                // the warp-stream kernel ran (other comb kernels: serial path below)
+          if (marked) {
             AMTK_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side, 0));
-            if (ctx->stream_wait_value32(reinterpret_cast<CUstream>(ctx->side_stream), (CUdeviceptr)(uintptr_t)ctx->side_flag, 1u, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-              AMTK_FAIL("cuStreamWaitValue32 failed");
             cudaStream_t main_stream = ctx->stream;
             ctx->stream = ctx->side_stream;                  // the context is locked (DevSelect): nobody else sees the swap
             const int ok = scan_frames_impl(ctx, clip, clip, 0, 0, logos, nlogos, w, lo, hi, 0, ds_, frame0);

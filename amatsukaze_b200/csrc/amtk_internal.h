@@ -11,7 +11,6 @@
 #include "logo_host.h"
 
 // cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no link-time dependency on libcuda.so).
-typedef CUresult (*amtk_stream_wait_value32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 typedef CUresult (*amtk_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -68,13 +67,11 @@ struct amtk_ctx {
   void* dout = nullptr; size_t dout_bytes = 0;             // device-side outputs when the caller's are on the host
   void* dout2 = nullptr; size_t dout2_bytes = 0;
   amtk_encode_tiled_fn encode_tiled = nullptr;
-  amtk_stream_wait_value32_fn stream_wait_value32 = nullptr;   // cuStreamWaitValue32: the side stream waits for "all comb CTAs resident"
-  bool want_side_mark = false;                // fused step: the next warp-stream comb launch records ev_side right before its kernel ...
-  const void* side_flag = nullptr;            // ... and leaves here the device word its CTAs raise once all of them are resident
+  bool want_side_mark = false;                // fused step (opt-in overlap): the next warp-stream comb launch records ev_side right before its kernel
   struct Knobs {            // kernel-variant selection; read from AMTK_* environment variables at context creation
     int eval_waves = 1;     // logo_scores_kernel CTAs per SM
     int eval_cw = 1;        // 1: 64-pixel-wide logos use the compile-time-width kernel variant
-    int scan_overlap = 1;   // fused step on resident clips: logo kernels on the side stream, packed into the comb kernel's tail
+    int scan_overlap = 0;   // 1: fused step on resident clips: logo kernels on the side stream (faster step, but stretches the comb kernel's own duration)
     int comb_generic = 0;   // 1: force the plain-load comb kernel
     int comb_merge_uv = 1;  // U|V remainder columns share one tile
     int comb_part = -1;     // partition: -1 auto, 0 equal-share, 1 lock-step

@@ -359,9 +359,6 @@ __global__ void __launch_bounds__(32 * Cfg::WARPS, Cfg::MIN_CTAS) comb_ws_kernel
     for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // "all CTAs of this launch are resident": word 33 of the queue block goes to 1 when the last CTA has checked in (the
-  // fused step's side stream waits for it before the logo kernels may take SMs; a.queue[32..33] are zeroed per launch)
-  if (threadIdx.x == 0 && atomicAdd(a.queue + 32, 1) == (int)gridDim.x - 1) { __threadfence(); atomicExch(a.queue + 33, 1); }
   __syncwarp();
   // warp streams are independent from here on: no block-level synchronisation, work comes from a global queue of
   // (tile, frame range) items (long items first, short ones last, so the warps finish within a short item of each other)
