@@ -474,18 +474,25 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
   const int grid = (int)std::min<long long>((long long)ctx->sm_count * occ, (total + WW - 1) / WW);
   const int f0 = lo - win.first;
   if (!(plan.valid && plan.wY == wY && plan.hY == hY && plan.wC == wC && plan.hC == hC && plan.nf == nf && plan.f0 == f0 &&
-        plan.R == V->R + 100 * bps && plan.item == ctx->knobs.comb_item && plan.ctas == occ * WW)) {
+        plan.R == V->R + 100 * bps && plan.item == ctx->knobs.comb_item + 1000 * ctx->knobs.comb_tail && plan.ctas == occ * WW)) {
     int big = ctx->knobs.comb_item > 0 ? ctx->knobs.comb_item : 64, small = std::max(4, big / 4);
     // each warp should see at least ~6 big items; shrink for short clips
     while (big > 8 && (long long)ntiles * (nf / big) < 6LL * nwarps) { big /= 2; small = std::max(4, big / 4); }
     const int tail_frames = std::min(nf, std::max(small, (int)(nf * 0.15)));
     const int head_frames = nf - tail_frames;
+    // third tier (AMTK_COMB_TAIL = frames per item, 0 = off): the last ~4 % of the frames in very short items, so that the warps
+    // run dry within one such item of each other (a 16-frame item is ~48 us of a warp stream's time; measured -1.2 %)
+    const int tiny = ctx->knobs.comb_tail;
+    const int end_frames = (tiny > 0 && tiny < small) ? std::min(tail_frames, std::max(tiny, (int)(nf * 0.04))) : 0;
+    const int mid_end = nf - end_frames;
     std::vector<CombSegment> segs;
-    segs.reserve((size_t)ntiles * (head_frames / big + tail_frames / small + 2));
+    segs.reserve((size_t)ntiles * (head_frames / big + tail_frames / small + (tiny > 0 ? end_frames / tiny : 0) + 3));
     for (int t = 0; t < ntiles; ++t)
       for (int f = 0; f < head_frames; f += big) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(head_frames, f + big) });
     for (int t = 0; t < ntiles; ++t)
-      for (int f = head_frames; f < nf; f += small) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(nf, f + small) });
+      for (int f = head_frames; f < mid_end; f += small) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(mid_end, f + small) });
+    for (int t = 0; t < ntiles; ++t)
+      for (int f = mid_end; f < nf; f += tiny) segs.push_back(CombSegment{ t, f0 + f, f0 + std::min(nf, f + tiny) });
     const size_t seg_bytes = segs.size() * sizeof(CombSegment);
     plan.q_off = (seg_bytes + 255) & ~(size_t)255;
     plan.valid = false;
@@ -494,7 +501,7 @@ static int launch_comb_ws(amtk_ctx* ctx, const amtk_clip* clip, const Window& wi
     AMTK_CUDA(cudaStreamSynchronize(ctx->stream));           // pageable source vector dies at the end of this scope
     plan.nitems = (int)segs.size();
     plan.wY = wY; plan.hY = hY; plan.wC = wC; plan.hC = hC; plan.nf = nf; plan.f0 = f0; plan.R = V->R + 100 * bps;
-    plan.item = ctx->knobs.comb_item; plan.ctas = occ * WW; plan.valid = true;
+    plan.item = ctx->knobs.comb_item + 1000 * ctx->knobs.comb_tail; plan.ctas = occ * WW; plan.valid = true;
   }
   AMTK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(plan.dev) + plan.q_off, 0, 256, ctx->stream));
   args.segs = reinterpret_cast<const CombSegment*>(plan.dev);
@@ -858,6 +865,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_LITE_CTAS")) c->knobs.lite_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("AMTK_COMB_WS_STAGES")) c->knobs.comb_ws_stages = atoi(e);
   if (const char* e = getenv("AMTK_COMB_ITEM")) c->knobs.comb_item = atoi(e);
+  if (const char* e = getenv("AMTK_COMB_TAIL")) c->knobs.comb_tail = atoi(e);
   if (const char* e = getenv("AMTK_COMB_MMA")) c->knobs.comb_mma = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS10")) c->knobs.comb_ws10 = atoi(e);
   if (const char* e = getenv("AMTK_EVAL_CW")) c->knobs.eval_cw = atoi(e);

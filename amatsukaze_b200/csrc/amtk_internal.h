@@ -77,6 +77,7 @@ struct amtk_ctx {
     int comb_part = -1;     // partition: -1 auto, 0 equal-share, 1 lock-step
     int comb_strip = 8, comb_stages = 3, comb_R = 0, comb_ctas = 0, comb_sync = 0, comb_l2 = 64;
     int comb_item = 0;        // frames per long work item of the warp-stream kernel (0 = auto)
+    int comb_tail = 4;        // third tier of the work queue: items of this many frames over the last ~4 % of the range (0 = two tiers; measured -1.2 %)
     int comb_ws_stages = 2;  // ring slots per warp stream
     int comb_mma = 0;        // 1|2: tensor-core streaming kernel (comb_mma.cuh) for 8-bit clips, NS tiles per CTA step
     int comb_ws10 = 1;       // 16-bit containers with <= 10 significant bits run the warp-stream kernel's integer-lane form

@@ -245,12 +245,47 @@ def timed_ms(torch, stream, fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def secondary_configs(torch, ab, synth, ctx, stream, device, which, peak):
-    """configs[2] (1440x1080 3600-field combing pass), configs[3] (LogoScan accumulation over 10000 1080p frames),
-    AMTAnalyzeLogo (33 evaluations per frame) and LogoFrame::ScanFrame alone, each device resident."""
+def secondary_configs(torch, ab, synth, ctx, stream, device, which, peak, po=None):
+    """configs[0] (one 1440x1080 frame, 64x64 template: call latency), configs[2] (1440x1080 3600-field combing pass),
+    configs[3] (LogoScan accumulation over 10000 1080p frames), AMTAnalyzeLogo (33 evaluations per frame) and
+    LogoFrame::ScanFrame alone, each device resident.  `po` (the oracle module) is passed only by the cpu_baseline leg."""
+    import numpy as np
     out = {}
     lg = synth.make_logo(LOGO_W, LOGO_H)
     with torch.cuda.stream(stream):
+        if "single_frame_1440" in which:
+            # configs[0]: ONE 1440x1080 YV12 frame, 64x64 template at (1280, 64), DeintY + EvaluateLogo(fade 0) + EvaluateLogo(fade 1)
+            # (SURVEY 8(d) config 1).  This is a latency case: one GetFrame-sized call through the C ABI.
+            w, h, ix, iy = 1440, 1080, 1280, 64
+            t = make_clip(torch, synth, lg, device, SEED + 3, w, h, 1, imgx=ix, imgy=iy)
+            logo1 = ab.Logo.create(lg["data"], LOGO_W, LOGO_H, w, h, ix, iy).deint().create_mask(MASKRATIO)
+            hfr = torch.empty((1, w * h * 3 // 2), dtype=torch.uint8, pin_memory=True)
+            hfr.copy_(t)
+            torch.cuda.synchronize()
+            dclip, hclip = ab.yv12_clip(t, w, h, 1, True), ab.yv12_clip(hfr, w, h, 1, on_device=False)
+            hs, hd = np.empty((1, 1, 2), np.float32), np.empty((1, 1, 2), np.float32)
+            reps = 300
+            for clip1, dst, key in ((hclip, hs, "host_frame_us_per_call"), (dclip, hd, "resident_frame_us_per_call")):
+                for _ in range(20):
+                    ctx.scan_frames(clip1, [logo1], out=dst)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    ctx.scan_frames(clip1, [logo1], out=dst)        # blocking: returns after the D2H of the two scores
+                out.setdefault("single_frame_1440", {})[key] = (time.perf_counter() - t0) / reps * 1e6
+            e = out["single_frame_1440"]
+            e["workload"] = "configs[0]: one 1440x1080 YV12 frame, 64x64 template at (1280,64), ScanFrame (2 evaluations), wall clock per blocking C-ABI call"
+            e["h2d_bytes_per_call_host_frame"] = ctx.last_h2d_bytes if hasattr(ctx, "last_h2d_bytes") else None
+            e["host_equals_resident"] = bool(np.array_equal(hs.view(np.uint32), hd.view(np.uint32)))
+            if po is not None:
+                b1 = po.CpuBench(w, h, lg["data"], ix, iy, 1, MASKRATIO)
+                fr = np.repeat(hfr.numpy(), 64, axis=0)
+                sec, sc, _ = min((b1.run(fr, [20, 12, 36, 24, 16, 48], 1, "avx2") for _ in range(3)), key=lambda r: r[0])
+                e["cpu_us_per_frame_1_thread"] = sec / 64 * 1e6
+                e["cpu_code"] = "reference's own ComputeKernel.cpp/LogoScan.hpp (oracle/_ref)" if b1.kind == "reference" else "C port (oracle/amtk_oracle.c)"
+                e["scores_bitexact_vs_cpu"] = bool(np.array_equal(sc[:1].view(np.uint32), hd.reshape(1, 2).view(np.uint32)))
+                b1.close()
+            del t, hfr
         if "comb_1440" in which:
             w, h, n = 1440, 1080, 1800
             t = make_clip(torch, synth, None, device, SEED, w, h, n, mode="telecine")
@@ -437,7 +472,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="headline",
-                    choices=["headline", "comb_1440", "comb_p10", "logoscan_10k", "logo_analyze", "logo_scan", "secondary"])
+                    choices=["headline", "single_frame_1440", "comb_1440", "comb_p10", "logoscan_10k", "logo_analyze", "logo_scan", "secondary"])
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU reference arm (0 = 8 per thread, 96..1800)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
@@ -473,7 +508,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
 
     if args.config != "headline":
-        which = ["comb_1440", "comb_p10", "logoscan_10k", "logo_analyze", "logo_scan"] if args.config == "secondary" else [args.config]
+        which = ["single_frame_1440", "comb_1440", "comb_p10", "logoscan_10k", "logo_analyze", "logo_scan"] if args.config == "secondary" else [args.config]
         res = secondary_configs(torch, ab, synth, ctx, stream, device, which, peak)
         if rank == 0:
             print(json.dumps({"config": args.config, "n_gpus": 1, "data": "synthetic", "timing": "CUDA events on the launch stream, device-resident inputs",
@@ -646,7 +681,8 @@ def main():
         if not args.no_secondary and world == 1:
             del clip_t
             torch.cuda.empty_cache()
-            secondary = secondary_configs(torch, ab, synth, ctx, stream, device, ["comb_1440", "comb_p10", "logoscan_10k", "logo_analyze", "logo_scan"], peak)
+            secondary = secondary_configs(torch, ab, synth, ctx, stream, device, ["single_frame_1440", "comb_1440", "comb_p10", "logoscan_10k", "logo_analyze", "logo_scan"], peak,
+                                          po=None if args.no_cpu else po)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
