@@ -211,6 +211,18 @@ struct EvalSpec {
   int out_off, out_fade_stride;     // where in an output row the values go
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is sticky per (device, kernel): set it once, raise it when a larger logo comes along
+static bool want_smem(amtk_ctx* ctx, const void* fn, int bytes) {
+  for (auto& e : ctx->smem_attr) if (e.first == fn) {
+    if (e.second >= bytes) return true;
+    if (!cuda_ok(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute")) return false;
+    e.second = bytes; return true;
+  }
+  if (!cuda_ok(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute")) return false;
+  ctx->smem_attr.emplace_back(fn, bytes);
+  return true;
+}
+
 static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, int lo, int hi, int pitch_elems,
                        const EvalSpec& sp, float* dout, int out_frame_stride, int out_row0) {
   const amtk::HostLogo& hl = sp.logo->host;
@@ -281,7 +293,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
 #define AMTK_LAUNCH_SCORES(T, P)                                                                              \
   do {                                                                                                        \
     void (*kfn)(const EvalJob) = wh64 ? logo_scores_kernel<T, P, 64, 64> : w64 ? logo_scores_kernel<T, P, 64, 0> : logo_scores_kernel<T, P, 0, 0>; \
-    AMTK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    if (!want_smem(ctx, (const void*)kfn, (int)smem)) return 0;                                                \
     kfn<<<grid, kEvalThreads, smem, ctx->stream>>>(job);                                                      \
   } while (0)
     if (!u16) { if (pxt == 1) AMTK_LAUNCH_SCORES(uint8_t, 1); else if (pxt == 2) AMTK_LAUNCH_SCORES(uint8_t, 2); else AMTK_LAUNCH_SCORES(uint8_t, 3); }
@@ -292,7 +304,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     float* sum_out = dout + (size_t)(f0 - out_row0) * out_frame_stride;
     const size_t sum_smem = (size_t)32 * (countPad + 4) * sizeof(float);
     if (sum_smem <= 200 * 1024) {
-      AMTK_CUDA(cudaFuncSetAttribute(logo_sum_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
+      if (!want_smem(ctx, (const void*)logo_sum_bulk_kernel, (int)sum_smem)) return 0;
       logo_sum_bulk_kernel<<<(total + 31) / 32, 32, sum_smem, ctx->stream>>>(
           job.scores, count, countPad, n, sp.nfades, hl.blackScore, sp.take_abs, sum_out, out_frame_stride, sp.out_off, sp.out_fade_stride);
     } else {
@@ -891,6 +903,7 @@ void amtk_ctx_destroy(amtk_ctx* c) {
   if (c->small) cudaFree(c->small);
   if (c->dout) cudaFree(c->dout);
   if (c->dout2) cudaFree(c->dout2);
+  if (c->hout) cudaFreeHost(c->hout);
   if (c->plan.dev) cudaFree(c->plan.dev);
   for (auto* v : { &c->timing_events, &c->timing_pool }) for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1133,8 +1146,33 @@ int amtk_logo_get_tables(const amtk_logo* l, float* data, uint8_t* mask, float* 
 // ---------------------------------------------------------------------------------------------------------
 // evaluation entry points
 // ---------------------------------------------------------------------------------------------------------
+// Small host outputs (a GetFrame-sized call returns 8 .. 1056 bytes): the result kernels write straight into a pinned, device-mapped
+// buffer of the context, so the call ends with a stream synchronise and a CPU copy instead of a D2H copy operation and ITS
+// completion (a third of a one-frame call's wall time).  Only for outputs that kernels write once (logo scores), never for the
+// atomically accumulated combing counters.
+constexpr size_t kHostOutBytes = 64 << 10;
+static float* host_out_alias(amtk_ctx* ctx, size_t bytes) {
+  if (bytes > kHostOutBytes) return nullptr;
+  if (!ctx->hout) {
+    if (cudaHostAlloc(&ctx->hout, kHostOutBytes, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); ctx->hout = nullptr; return nullptr; }
+    if (cudaHostGetDevicePointer(&ctx->hout_dev, ctx->hout, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(ctx->hout); ctx->hout = nullptr; return nullptr; }
+  }
+  return reinterpret_cast<float*>(ctx->hout_dev);
+}
+// device buffer the result kernels of a host-output call write to: the mapped alias when the output is small, else ctx->dout
+static float* host_out_buffer(amtk_ctx* ctx, size_t bytes) {
+  if (float* a = host_out_alias(ctx, bytes)) return a;
+  if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return nullptr;
+  return reinterpret_cast<float*>(ctx->dout);
+}
+
 static int finish_output(amtk_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes, int out_on_device) {
   if (out_on_device) return 1;
+  if (ctx->hout && dev_src == ctx->hout_dev) {
+    AMTK_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(host_dst, ctx->hout, bytes);
+    return 1;
+  }
   AMTK_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   AMTK_CUDA(cudaStreamSynchronize(ctx->stream));
   return 1;
@@ -1184,7 +1222,7 @@ int amtk_logo_scan_frames(amtk_ctx* ctx, const amtk_clip* clip, amtk_logo* const
   DevSelect ds(ctx); if (!ds.ok) return 0;
   const size_t bytes = (size_t)nframes * nlogos * 2 * sizeof(float);
   float* d = out;
-  if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
+  if (!out_on_device) { d = host_out_buffer(ctx, bytes); if (!d) return 0; }
   int rx, ry, rw, rh;
   if (!clip->on_device && pitch_override <= 0 && logos_bbox(clip, logos, nlogos, &rx, &ry, &rw, &rh)) {
     // host frames: only the logo rectangles cross PCIe (the reference reads nothing else, LogoScan.hpp:1559-1566)
@@ -1223,7 +1261,7 @@ int amtk_logo_analyze_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_lo
   DevSelect ds(ctx); if (!ds.ok) return 0;
   const size_t bytes = (size_t)nframes * 33 * sizeof(float);
   float* d = out;
-  if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
+  if (!out_on_device) { d = host_out_buffer(ctx, bytes); if (!d) return 0; }
   if (!roi_inside(dl->host, clip, clip->pitch_y / clip->bytes_per_sample)) AMTK_FAIL("logo rectangle lies outside the frame");
   if (!for_each_roi_window(ctx, clip, frame0, nframes, dl->host.imgx, dl->host.imgy, dl->host.w, dl->host.h, false, false,
                            [&](const amtk_clip& v, const Window& w, int lo, int hi, int dx, int dy) {
@@ -1241,7 +1279,7 @@ int amtk_logo_eval_fades(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* 
   DevSelect ds(ctx); if (!ds.ok) return 0;
   const size_t bytes = (size_t)nframes * nfades * sizeof(float);
   float* d = out;
-  if (!out_on_device) { if (!ensure(&ctx->dout, &ctx->dout_bytes, bytes)) return 0; d = reinterpret_cast<float*>(ctx->dout); }
+  if (!out_on_device) { d = host_out_buffer(ctx, bytes); if (!d) return 0; }
   const int pitch = clip->pitch_y / clip->bytes_per_sample;
   if (!roi_inside(dl->host, clip, pitch)) AMTK_FAIL("logo rectangle lies outside the frame");
   if (!for_each_roi_window(ctx, clip, frame0, nframes, dl->host.imgx, dl->host.imgy, dl->host.w, dl->host.h, false, false,

@@ -123,10 +123,11 @@ def test_logoscan_10000_frames_1080p(ctx, oracle):
 
 @pytest.mark.timeout(900)
 def test_whole_clip_1080p_against_reference_code(ctx, oracle):
-    """300 consecutive 1080p frames of the bench clip: every logo score bit-identical with the reference's own compiled
-    code, every combing counter identical with the spec (AVX2 form; scalar form on a subset)."""
+    """1000 consecutive 1080p frames of the bench clip (enough for all three tiers of the streaming kernel's work queue:
+    32-, 8- and 4-frame items): every logo score bit-identical with the reference's own compiled code, every combing
+    counter identical with the spec (AVX2 form; scalar form on a subset)."""
     po = oracle
-    w, h, n, imgx, imgy = 1920, 1080, 300, 1700, 60
+    w, h, n, imgx, imgy = 1920, 1080, 1000, 1700, 60
     lg = synth.make_logo(64, 64)
     fr = _gen(0, n, w, h, logo=lg, imgx=imgx, imgy=imgy)
     logo = ab.Logo.create(lg["data"], 64, 64, w, h, imgx, imgy).deint().create_mask(0.35)
