@@ -286,6 +286,39 @@ def secondary_configs(torch, ab, synth, ctx, stream, device, which, peak, po=Non
                 e["scores_bitexact_vs_cpu"] = bool(np.array_equal(sc[:1].view(np.uint32), hd.reshape(1, 2).view(np.uint32)))
                 b1.close()
             del t, hfr
+            # AMTAnalyzeLogo::GetFrame (LogoScan.hpp:1119-1161): ONE output frame = 8 source frames x 33 evaluations
+            # (deint logo + two field logos x 11 fades), the call AviSynth makes; 8 host frames in, 1056 bytes out
+            t8 = make_clip(torch, synth, lg, device, SEED + 5, w, h, 8, imgx=ix, imgy=iy)
+            raw = ab.Logo.create(lg["data"], LOGO_W, LOGO_H, w, h, ix, iy)
+            de, top, bot = raw.deint().create_mask(MASKRATIO), raw.field(0).create_mask(MASKRATIO), raw.field(1).create_mask(MASKRATIO)
+            h8 = torch.empty((8, w * h * 3 // 2), dtype=torch.uint8, pin_memory=True)
+            h8.copy_(t8)
+            torch.cuda.synchronize()
+            hclip8 = ab.yv12_clip(h8, w, h, 8, on_device=False)
+            ha = np.empty((8, 33), np.float32)
+            for _ in range(10):
+                ctx.analyze_frames(hclip8, de, top, bot, out=ha)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(100):
+                ctx.analyze_frames(hclip8, de, top, bot, out=ha)
+            g = {"workload": "AMTAnalyzeLogo::GetFrame: one output frame = 8 host source frames (1440x1080) x 33 evaluations, wall clock per blocking C-ABI call",
+                 "us_per_call": (time.perf_counter() - t0) / 100 * 1e6, "h2d_bytes_per_call": ctx.last_h2d_bytes, "d2h_bytes_per_call": int(ha.nbytes)}
+            if po is not None and po.ref_available():
+                rl = po.RefLogo.create(lg["data"], LOGO_W, LOGO_H, w, h, ix, iy)
+                rde, rtop, rbot = rl.deint().create_mask(MASKRATIO), rl.field(0).create_mask(MASKRATIO), rl.field(1).create_mask(MASKRATIO)
+                Y8 = h8.numpy()[:, : w * h].reshape(8, h, w)
+                best, ra = None, None
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    ra = np.stack([po.ref_analyze_frame(rde, rtop, rbot, Y8[i]) for i in range(8)])
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                g["cpu_us_per_call_1_thread"] = best * 1e6
+                g["cpu_code"] = "reference's own DeintY/CopyY/EvaluateLogo (oracle/_ref), 33 x 8 calls through ctypes (a few % of binding overhead)"
+                g["bitexact_vs_cpu"] = bool(np.array_equal(ra.view(np.uint32), ha.view(np.uint32)))
+            out["analyze_getframe_1440"] = g
+            del t8, h8
         if "comb_1440" in which:
             w, h, n = 1440, 1080, 1800
             t = make_clip(torch, synth, None, device, SEED, w, h, n, mode="telecine")
