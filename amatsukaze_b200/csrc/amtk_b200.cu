@@ -266,7 +266,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
   // frames per launch bounded by the score scratch (<= 96 MB)
   const size_t per_frame = (size_t)sp.nfades * countPad * sizeof(float);
   const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)(hi - lo), ((size_t)96 << 20) / per_frame));
-  if (!ensure(&ctx->scratch, &ctx->scratch_bytes, per_frame * batch)) return 0;
+  if (!ensure(&ctx->scratch, &ctx->scratch_bytes, ctx->scratch_off + per_frame * batch)) return 0;
   for (int f0 = lo; f0 < hi; f0 += batch) {
     const int n = std::min(batch, hi - f0);
     EvalJob job;
@@ -277,7 +277,7 @@ static int launch_eval(amtk_ctx* ctx, const amtk_clip* clip, const Window& win, 
     job.src_mode = sp.src_mode; job.src_off = sp.src_off; job.src_stride = sp.src_stride;
     job.logo = logo_dev(sp.logo); job.maxv = maxv; job.nfades = sp.nfades;
     for (int i = 0; i < sp.nfades; ++i) job.fades[i] = sp.fades[i];
-    job.scores = reinterpret_cast<float*>(ctx->scratch);
+    job.scores = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->scratch) + ctx->scratch_off);
     job.use_tma = tma_ok ? 1 : 0; job.roi_box_w = box_w; job.roi_box_x = box_x; job.roi_map = roi_map;
     job.ab_smem = ab_smem; job.pair_fades = pair_fades;
     const int slices3 = (count + kEvalThreads * 3 - 1) / (kEvalThreads * 3);
@@ -849,7 +849,11 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   bool ok = cuda_ok(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)") &&
             cuda_ok(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking), "cudaStreamCreate(side)") &&
             cuda_ok(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming), "cudaEventCreate") &&
-            cuda_ok(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming), "cudaEventCreate");
+            cuda_ok(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming), "cudaEventCreate") &&
+            cuda_ok(cudaStreamCreateWithFlags(&c->side_stream2, cudaStreamNonBlocking), "cudaStreamCreate(side2)") &&
+            cuda_ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate") &&
+            cuda_ok(cudaEventCreateWithFlags(&c->ev_join1, cudaEventDisableTiming), "cudaEventCreate") &&
+            cuda_ok(cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming), "cudaEventCreate");
   for (int b = 0; b < 2 && ok; ++b) {
     ok = cuda_ok(cudaEventCreateWithFlags(&c->ev_copy[b], cudaEventDisableTiming), "cudaEventCreate") &&
          cuda_ok(cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming), "cudaEventCreate");
@@ -881,6 +885,7 @@ int amtk_ctx_create(int device, void* cuda_stream, amtk_ctx** out) {
   if (const char* e = getenv("AMTK_COMB_MMA")) c->knobs.comb_mma = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS10")) c->knobs.comb_ws10 = atoi(e);
   if (const char* e = getenv("AMTK_EVAL_CW")) c->knobs.eval_cw = atoi(e);
+  if (const char* e = getenv("AMTK_EVAL_PAR")) c->knobs.eval_par = atoi(e);
   if (const char* e = getenv("AMTK_SCAN_OVERLAP")) c->knobs.scan_overlap = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS_WARPS")) c->knobs.comb_ws_warps = atoi(e);
   if (const char* e = getenv("AMTK_COMB_WS_PF")) c->knobs.comb_ws_prefetch = atoi(e);
@@ -898,6 +903,8 @@ void amtk_ctx_destroy(amtk_ctx* c) {
   if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
   if (c->ev_side) cudaEventDestroy(c->ev_side);
   if (c->ev_side_done) cudaEventDestroy(c->ev_side_done);
+  if (c->side_stream2) { cudaStreamSynchronize(c->side_stream2); cudaStreamDestroy(c->side_stream2); }
+  for (cudaEvent_t e : { c->ev_fork, c->ev_join1, c->ev_join2 }) if (e) cudaEventDestroy(e);
   for (int b = 0; b < 2; ++b) { if (c->ev_copy[b]) cudaEventDestroy(c->ev_copy[b]); if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->stage[b]) cudaFree(c->stage[b]); }
   if (c->scratch) cudaFree(c->scratch);
   if (c->small) cudaFree(c->small);
@@ -1246,9 +1253,36 @@ static int analyze_impl(amtk_ctx* ctx, const amtk_clip* clip, int dx, int dy, co
   EvalSpec sp{ dl, rx, ry, w, h, 0, 0, w, 11, fades, 1, 0, 1 };                // p[f]: deint logo on DeintY
   EvalSpec st{ ft, rx, ry, w, h, 1, 0, 2 * w, 11, fades, 1, 11, 1 };           // t[f]: top field logo on CopyY, stride 2w
   EvalSpec sb{ fb, rx, ry, w, h, 1, w, 2 * w, 11, fades, 1, 22, 1 };           // b[f]: bottom field logo on CopyY + w
-  return launch_eval(ctx, clip, win, lo, hi, pitch, sp, dout, 33, row0) &&
-         launch_eval(ctx, clip, win, lo, hi, pitch, st, dout, 33, row0) &&
-         launch_eval(ctx, clip, win, lo, hi, pitch, sb, dout, 33, row0);
+  const int n = hi - lo;
+  if (!(ctx->knobs.eval_par && n <= 16 && ctx->side_stream && ctx->side_stream2))
+    return launch_eval(ctx, clip, win, lo, hi, pitch, sp, dout, 33, row0) &&
+           launch_eval(ctx, clip, win, lo, hi, pitch, st, dout, 33, row0) &&
+           launch_eval(ctx, clip, win, lo, hi, pitch, sb, dout, 33, row0);
+  // GetFrame-sized call (AMTAnalyzeLogo::GetFrame = 8 source frames): each evaluation launches only n CTAs, so the three of them
+  // run side by side on three streams, each with its own slice of the score scratch (115 -> ~70 us per call).  The context is
+  // locked for the whole entry point (DevSelect), so swapping ctx->stream around a launch is invisible to other threads.
+  const EvalSpec* specs[3] = { &sp, &st, &sb };
+  size_t off[3], total = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (!logo_ensure_device(specs[i]->logo, ctx, true)) return 0;                      // table uploads happen before the fork
+    off[i] = total;
+    total += (((size_t)n * 11 * specs[i]->logo->countPad * sizeof(float)) + 255) & ~(size_t)255;
+  }
+  if (!ensure(&ctx->scratch, &ctx->scratch_bytes, total)) return 0;                    // no reallocation once work is in flight
+  cudaStream_t main_stream = ctx->stream, streams[3] = { ctx->stream, ctx->side_stream, ctx->side_stream2 };
+  cudaEvent_t joins[3] = { nullptr, ctx->ev_join1, ctx->ev_join2 };
+  AMTK_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+  int ok = 1;
+  for (int i = 0; i < 3 && ok; ++i) {
+    if (i) ok = cuda_ok(cudaStreamWaitEvent(streams[i], ctx->ev_fork, 0), "cudaStreamWaitEvent");
+    ctx->stream = streams[i]; ctx->scratch_off = off[i];
+    ok = ok && launch_eval(ctx, clip, win, lo, hi, pitch, *specs[i], dout, 33, row0);
+    ctx->stream = main_stream; ctx->scratch_off = 0;
+    if (i && ok) ok = cuda_ok(cudaEventRecord(joins[i], streams[i]), "cudaEventRecord") &&
+                      cuda_ok(cudaStreamWaitEvent(main_stream, joins[i], 0), "cudaStreamWaitEvent");
+  }
+  if (!ok) { cudaStreamSynchronize(ctx->side_stream); cudaStreamSynchronize(ctx->side_stream2); }   // nothing of this call stays in flight
+  return ok;
 }
 
 int amtk_logo_analyze_frames(amtk_ctx* ctx, const amtk_clip* clip, const amtk_logo* dl, const amtk_logo* ft, const amtk_logo* fb,

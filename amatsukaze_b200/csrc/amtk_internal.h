@@ -55,6 +55,9 @@ struct amtk_ctx {
   cudaStream_t copy_stream = nullptr;       // H2D staging for host-resident clips
   cudaStream_t side_stream = nullptr;       // the logo evaluation that runs UNDER the streaming comb kernel (fused step)
   cudaEvent_t ev_side = nullptr, ev_side_done = nullptr;
+  cudaStream_t side_stream2 = nullptr;      // GetFrame-sized AMTAnalyzeLogo calls: the three logo evaluations run side by side (main + two side streams)
+  cudaEvent_t ev_fork = nullptr, ev_join1 = nullptr, ev_join2 = nullptr;
+  size_t scratch_off = 0;                   // byte offset into `scratch` the next launch_eval writes its per-pixel scores at
   cudaEvent_t ev_copy[2] = { nullptr, nullptr };
   cudaEvent_t ev_done[2] = { nullptr, nullptr };
   int sm_count = 0;
@@ -73,6 +76,7 @@ struct amtk_ctx {
   struct Knobs {            // kernel-variant selection; read from AMTK_* environment variables at context creation
     int eval_waves = 1;     // logo_scores_kernel CTAs per SM
     int eval_cw = 1;        // 1: 64-pixel-wide logos use the compile-time-width kernel variant
+    int eval_par = 1;       // 1: AMTAnalyzeLogo calls of <= 16 frames run their three evaluations concurrently on three streams
     int scan_overlap = 0;   // 1: fused step on resident clips: logo kernels on the side stream (faster step, but stretches the comb kernel's own duration)
     int comb_generic = 0;   // 1: force the plain-load comb kernel
     int comb_merge_uv = 1;  // U|V remainder columns share one tile
