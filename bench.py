@@ -318,7 +318,37 @@ def secondary_configs(torch, ab, synth, ctx, stream, device, which, peak, po=Non
                 g["cpu_code"] = "reference's own DeintY/CopyY/EvaluateLogo (oracle/_ref), 33 x 8 calls through ctypes (a few % of binding overhead)"
                 g["bitexact_vs_cpu"] = bool(np.array_equal(ra.view(np.uint32), ha.view(np.uint32)))
             out["analyze_getframe_1440"] = g
-            del t8, h8
+            # AMTEraseLogo::GetFrame (LogoScan.hpp:1343-1397): Delogo on the Y, U, V rectangles of ONE host frame, in place
+            # (per-field fades: the two-pass form); only the three rectangles cross PCIe, both ways
+            h1 = h8[:1].clone().pin_memory()
+            orig = h1.numpy().copy()
+            hclip1 = ab.yv12_clip(h1, w, h, 1, on_device=False)
+            fd = np.array([[0.3, 0.9]], np.float32)
+            for _ in range(10):
+                h1.numpy()[:] = orig
+                ctx.erase_logo(hclip1, raw, fd)
+            erased = h1.numpy().copy()
+            t0 = time.perf_counter()
+            for _ in range(100):
+                ctx.erase_logo(hclip1, raw, fd)                    # (erases the erased frame again: same work, timing only)
+            ge = {"workload": "AMTEraseLogo::GetFrame: Delogo of the 64x64 Y and 32x32 U, V rectangles of one 1440x1080 host frame, in place, per-field fades, wall clock per blocking C-ABI call",
+                  "us_per_call": (time.perf_counter() - t0) / 100 * 1e6, "h2d_bytes_per_call": ctx.last_h2d_bytes}
+            if po is not None:
+                ol = po.OracleLogo.create(lg["data"], LOGO_W, LOGO_H, w, h, ix, iy)
+                best, ref_fr = None, None
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    ref_fr = orig.copy()                           # the reference's MakeWritable: a full-frame copy (:1347)
+                    Yp, Up, Vp = (ref_fr[0, : w * h].reshape(h, w), ref_fr[0, w * h: w * h * 5 // 4].reshape(h // 2, w // 2),
+                                  ref_fr[0, w * h * 5 // 4:].reshape(h // 2, w // 2))
+                    po.or_erase_frame(ol, Yp, Up, Vp, 0.3, 0.9)
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                ge["cpu_us_per_frame_1_thread"] = best * 1e6
+                ge["cpu_code"] = "C port of Delogo/GetFrameT (oracle/amtk_oracle.c) + the full-frame MakeWritable copy the reference makes"
+                ge["bytes_equal_vs_cpu"] = bool(np.array_equal(erased, ref_fr))
+            out["erase_getframe_1440"] = ge
+            del t8, h8, h1
         if "comb_1440" in which:
             w, h, n = 1440, 1080, 1800
             t = make_clip(torch, synth, None, device, SEED, w, h, n, mode="telecine")
@@ -542,7 +572,10 @@ def main():
 
     if args.config != "headline":
         which = ["single_frame_1440", "comb_1440", "comb_p10", "logoscan_10k", "logo_analyze", "logo_scan"] if args.config == "secondary" else [args.config]
-        res = secondary_configs(torch, ab, synth, ctx, stream, device, which, peak)
+        po = None
+        if not args.no_cpu and "single_frame_1440" in which:     # the CPU figures beside the GetFrame-sized calls (cpu_baseline leg)
+            from oracle import pyoracle as po
+        res = secondary_configs(torch, ab, synth, ctx, stream, device, which, peak, po=po)
         if rank == 0:
             print(json.dumps({"config": args.config, "n_gpus": 1, "data": "synthetic", "timing": "CUDA events on the launch stream, device-resident inputs",
                               "peak_gbs": peak, "results": res}), flush=True)
