@@ -400,6 +400,13 @@ def ref_lib():
         R.ref_scan_get_logo.argtypes = [V, C.c_int, c_float_p]
         R.ref_logoframe_write.restype = C.c_int
         R.ref_logoframe_write.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int), c_float_p]
+        if hasattr(R, "ref_delogo_u8"):                         # round 2: AMTEraseLogo::Delogo / CalcFade2 (LogoScan.hpp:1248-1315)
+            R.ref_delogo_u8.restype = None
+            R.ref_delogo_u8.argtypes = [c_u8_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, c_float_p, C.c_float]
+            R.ref_delogo_u16.restype = None
+            R.ref_delogo_u16.argtypes = [c_u16_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, c_float_p, C.c_float]
+            R.ref_calc_fade2.restype = None
+            R.ref_calc_fade2.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
         R.ref_bench_create.restype = V
         R.ref_bench_create.argtypes = [V, C.c_int, C.c_int, C.c_int]
         R.ref_bench_free.argtypes = [V]
@@ -409,6 +416,40 @@ def ref_lib():
         R.ref_bench_scan_comb_u8.argtypes = [V, c_u8_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int, c_float_p, c_i32_p]
         _ref = R
     return _ref
+
+
+def ref_has_erase():
+    return ref_available() and hasattr(ref_lib(), "ref_delogo_u8")
+
+
+def ref_delogo(dst, A, B, fade, maxv, logopitch=None, imgpitch=None, w=None, h=None):
+    """The reference's own AMTEraseLogo::Delogo (LogoScan.hpp:1248-1261), in place on a C-contiguous u8/u16 array."""
+    a = dst
+    assert a.flags["C_CONTIGUOUS"]
+    A, B = _f32(A), _f32(B)
+    h = a.shape[0] if h is None else h
+    w = a.shape[1] if w is None else w
+    imgpitch = a.shape[1] if imgpitch is None else imgpitch
+    logopitch = w if logopitch is None else logopitch
+    if a.dtype == np.uint8:
+        ref_lib().ref_delogo_u8(_p(a, c_u8_p), w, h, logopitch, imgpitch, C.c_float(maxv), _p(A, c_float_p), _p(B, c_float_p), C.c_float(fade))
+    else:
+        ref_lib().ref_delogo_u16(_p(a, c_u16_p), w, h, logopitch, imgpitch, C.c_float(maxv), _p(A, c_float_p), _p(B, c_float_p), C.c_float(fade))
+    return a
+
+
+def ref_calc_fade2(records, num_frames, n):
+    """The reference's own AMTEraseLogo::CalcFade2 (LogoScan.hpp:1263-1315) over an analyze clip built from `records`
+    ((num_frames, 33) floats) the way AMTAnalyzeLogo lays it out: frame k = records of source frames 8k..8k+7, clamped to
+    the last source frame (:1133); GetFrame(n) outside the clip is clamped to its range (AviSynth's contract)."""
+    r = _f32(records).reshape(-1, 33)
+    N = r.shape[0]
+    nblocks = (N + 7) // 8
+    idx = np.minimum(np.arange(nblocks * 8), N - 1)
+    blocks = np.ascontiguousarray(r[idx])
+    ft, fb = C.c_float(), C.c_float()
+    ref_lib().ref_calc_fade2(_p(blocks, c_float_p), nblocks, int(num_frames), int(n), C.byref(ft), C.byref(fb))
+    return ft.value, fb.value
 
 
 def ref_logoframe(eval_results, frames_per_sec, outpath=None, num_candidates=-1):

@@ -6,6 +6,7 @@
  *   LogoScan.hpp:24-45      scalar CalcCorrelation5x5 + decl of the AVX one (ComputeKernel.cpp:77-121)
  *   LogoScan.hpp:59-660     LogoDataParam, approxim_line, LogoColor, LogoScan
  *   LogoScan.hpp:734-790    DeintLogo, DeintY, CopyY
+ *   LogoScan.hpp:1100-1103, 1248-1315   LogoAnalyzeFrame, AMTEraseLogo::Delogo + CalcFade2 (oracle/_ref/ref_erase.inc)
  * This file adds no arithmetic of its own: every function forwards to the extracted code.
  * `private`/`protected` are opened (oracle build only) so the tests can read the tables the reference
  * keeps private (scales, blackScore, LogoColor sums) -- SURVEY.md Appendix A item 4. */
@@ -180,6 +181,48 @@ int ref_logoframe_write(const float* eval /* [numFrames][numLogos][2] */, int nu
     if (outpath) lf.writeResult(outpath);
     return 1;
   } catch (const IOException&) { return 0; }
+}
+
+} /* extern "C" */
+
+/* ---- AMTEraseLogo::Delogo / CalcFade2 (LogoScan.hpp:1248-1315), verbatim inside a shim class.  The shim supplies what the two
+ * member functions touch: vi.num_frames, and an analyze clip whose GetFrame(n) hands out block n of a caller-provided array of
+ * LogoAnalyzeFrame records (8 per block, as AMTAnalyzeLogo lays them out, LogoScan.hpp:1128-1157). */
+#include <climits>
+#include "ref_analyzeframe.inc"
+struct RefShimFrameObj { const uint8_t* p; const uint8_t* GetReadPtr() const { return p; } };
+struct RefShimPFrame {
+  RefShimFrameObj o{ nullptr };
+  RefShimPFrame() {}
+  RefShimPFrame(std::nullptr_t) {}
+  explicit RefShimPFrame(const uint8_t* p) { o.p = p; }
+  const RefShimFrameObj* operator->() const { return &o; }
+};
+struct RefShimAnalyzeClip {
+  const LogoAnalyzeFrame* records; int nblocks;
+  RefShimPFrame GetFrame(int n, void*) const { return RefShimPFrame(reinterpret_cast<const uint8_t*>(records + (size_t)std::max(0, std::min(nblocks - 1, n)) * 8)); }
+};
+struct RefEraseShim {
+  struct { int num_frames; } vi;
+  const RefShimAnalyzeClip* analyzeclip;
+#define PVideoFrame RefShimPFrame
+#define IScriptEnvironment2 void
+#include "ref_erase.inc"
+#undef PVideoFrame
+#undef IScriptEnvironment2
+};
+extern "C" {
+void ref_delogo_u8(uint8_t* dst, int w, int h, int logopitch, int imgpitch, float maxv, const float* A, const float* B, float fade) {
+  RefEraseShim s; s.Delogo<uint8_t>(dst, w, h, logopitch, imgpitch, maxv, A, B, fade);
+}
+void ref_delogo_u16(uint16_t* dst, int w, int h, int logopitch, int imgpitch, float maxv, const float* A, const float* B, float fade) {
+  RefEraseShim s; s.Delogo<uint16_t>(dst, w, h, logopitch, imgpitch, maxv, A, B, fade);
+}
+/* records: [nblocks][8] LogoAnalyzeFrame = float[nblocks*8][33] */
+void ref_calc_fade2(const float* records, int nblocks, int num_frames, int n, float* fadeT, float* fadeB) {
+  RefShimAnalyzeClip clip{ reinterpret_cast<const LogoAnalyzeFrame*>(records), nblocks };
+  RefEraseShim s; s.vi.num_frames = num_frames; s.analyzeclip = &clip;
+  s.CalcFade2(n, *fadeT, *fadeB, nullptr);
 }
 
 /* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline / parity legs) ---------------------

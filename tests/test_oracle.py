@@ -156,3 +156,38 @@ def test_oracle_logoscan_equals_reference_live():
         assert (a is None) == (b is None)
         if a is not None:
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_delogo_and_calcfade2_equal_the_reference_code_live():
+    """Round 2: AMTEraseLogo::Delogo and CalcFade2 (LogoScan.hpp:1248-1315) are compiled from the reference's own lines into
+    oracle/_ref; the plain-C port (which the GPU erase kernel and the product's amtk_calc_fade2 are tested against) must
+    reproduce them exactly: pixel bytes for Delogo (rounding, clamping, per-field pitches), the selected fades for
+    CalcFade2 incl. the double-offset quirk (:1273-1275) and the clip-end clamps."""
+    if not po.ref_has_erase():
+        pytest.skip("prebuilt oracle/_ref predates the Delogo/CalcFade2 extraction")
+    rng = np.random.default_rng(11)
+    for dtype, maxv in ((np.uint8, 255.0), (np.uint16, 1023.0)):
+        for (w, h, lp, ip) in ((64, 64, 64, 96), (32, 16, 64, 200), (7, 5, 7, 7)):       # field passes: logopitch 2w, imgpitch 2*pitch
+            img = rng.integers(0, int(maxv) + 1, size=(h, ip)).astype(dtype)
+            A = rng.uniform(0.8, 1.6, size=h * lp).astype(np.float32)
+            B = rng.uniform(-0.6, 0.1, size=h * lp).astype(np.float32)
+            for fade in (0.0, 0.1, 0.3, 0.5, 0.9, 1.0):
+                a, b = img.copy(), img.copy()
+                po.or_delogo(a, A, B, fade, maxv, logopitch=lp, imgpitch=ip, w=w, h=h)
+                po.ref_delogo(b, A, B, fade, maxv, logopitch=lp, imgpitch=ip, w=w, h=h)
+                assert np.array_equal(a, b), (dtype, w, h, fade)
+                assert fade == 0.0 or not np.array_equal(a, img)
+    for N in (1, 5, 8, 9, 23, 64, 101):
+        rec = rng.uniform(0.0, 1.0, size=(N, 33)).astype(np.float32)
+        # sudden appear / disappear patterns so that both branches of :1295-1314 are taken
+        for k in range(N):
+            rec[k, : 11] += np.abs(np.arange(11) - (0 if (k // 7) % 2 == 0 else 10)) * np.float32(0.5)
+        took = set()
+        for n in range(N):
+            want = po.ref_calc_fade2(rec, N, n)
+            got = po.or_calc_fade2(rec, N, n)
+            assert got == want, (N, n, got, want)
+            took.add(want[0] == want[1])
+        if N >= 23:
+            assert took == {True, False}
