@@ -407,6 +407,13 @@ def ref_lib():
             R.ref_delogo_u16.argtypes = [c_u16_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, c_float_p, C.c_float]
             R.ref_calc_fade2.restype = None
             R.ref_calc_fade2.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p]
+        if hasattr(R, "ref_merge_field_u8"):                    # round 2: AMTSource::MergeField (AMTSource.hpp:291-355)
+            R.ref_merge_field_u8.restype = None
+            R.ref_merge_field_u8.argtypes = [c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int, c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int,
+                                             c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        if hasattr(R, "ref_erase_fades"):
+            R.ref_erase_fades.restype = C.c_int
+            R.ref_erase_fades.argtypes = [c_float_p, C.c_int, C.c_int, C.c_char_p, C.c_int, c_float_p, c_i32_p, C.c_char_p, C.c_int]
         R.ref_bench_create.restype = V
         R.ref_bench_create.argtypes = [V, C.c_int, C.c_int, C.c_int]
         R.ref_bench_free.argtypes = [V]
@@ -450,6 +457,52 @@ def ref_calc_fade2(records, num_frames, n):
     ft, fb = C.c_float(), C.c_float()
     ref_lib().ref_calc_fade2(_p(blocks, c_float_p), nblocks, int(num_frames), int(n), C.byref(ft), C.byref(fb))
     return ft.value, fb.value
+
+
+def _analyze_blocks(records):
+    r = _f32(records).reshape(-1, 33)
+    N = r.shape[0]
+    nblocks = (N + 7) // 8
+    return np.ascontiguousarray(r[np.minimum(np.arange(nblocks * 8), N - 1)]), nblocks
+
+
+def ref_erase_fades(records, num_frames, logof_path=None, max_fade_length=16):
+    """The reference's own AMTEraseLogo fade selection for every frame: ReadLogoFrameFile (LogoScan.hpp:1421-1461) when a
+    logoframe file is given, then CalcFade (:1317-1341, which falls back to CalcFade2).  Returns (fades (N,2) float32,
+    frameResult (N,) int32 or None); raises RuntimeError with the reference's ThrowError text."""
+    blocks, nblocks = _analyze_blocks(records)
+    out = np.zeros((num_frames, 2), np.float32)
+    fr = np.zeros(num_frames, np.int32)
+    err = C.create_string_buffer(512)
+    ok = ref_lib().ref_erase_fades(_p(blocks, c_float_p), nblocks, int(num_frames), str(logof_path).encode() if logof_path else None,
+                                   int(max_fade_length), _p(out, c_float_p), _p(fr, c_i32_p), err, 512)
+    if not ok:
+        raise RuntimeError(err.value.decode("utf-8", "replace"))
+    return out, (fr if logof_path else None)
+
+
+def ref_has_mergefield():
+    return ref_available() and hasattr(ref_lib(), "ref_merge_field_u8")
+
+
+def ref_merge_field(top, bottom, w, h, nv12=False):
+    """The reference's own AMTSource::MergeField (AMTSource.hpp:291-355) on two packed 8-bit 4:2:0 frames (1-D uint8 arrays:
+    Y then U, V planar -- or Y then interleaved UV when nv12): even rows from `top`, odd rows from `bottom`; returns the packed
+    planar YV12 frame."""
+    t = np.ascontiguousarray(top, np.uint8)
+    b = np.ascontiguousarray(bottom, np.uint8)
+    ysz, cw, ch = w * h, w // 2, h // 2
+    out = np.zeros(ysz + 2 * cw * ch, np.uint8)
+
+    def at(a, off):
+        return C.cast(a.ctypes.data + off, c_u8_p)
+    if nv12:
+        tu, tv, bu, bv, spuv = at(t, ysz), at(t, ysz), at(b, ysz), at(b, ysz), w
+    else:
+        tu, tv, bu, bv, spuv = at(t, ysz), at(t, ysz + cw * ch), at(b, ysz), at(b, ysz + cw * ch), cw
+    ref_lib().ref_merge_field_u8(at(out, 0), at(out, ysz), at(out, ysz + cw * ch), w, cw,
+                                 at(t, 0), tu, tv, w, spuv, at(b, 0), bu, bv, w, spuv, w, h, 1 if nv12 else 0)
+    return out
 
 
 def ref_logoframe(eval_results, frames_per_sec, outpath=None, num_candidates=-1):

@@ -6,7 +6,9 @@
  *   LogoScan.hpp:24-45      scalar CalcCorrelation5x5 + decl of the AVX one (ComputeKernel.cpp:77-121)
  *   LogoScan.hpp:59-660     LogoDataParam, approxim_line, LogoColor, LogoScan
  *   LogoScan.hpp:734-790    DeintLogo, DeintY, CopyY
- *   LogoScan.hpp:1100-1103, 1248-1315   LogoAnalyzeFrame, AMTEraseLogo::Delogo + CalcFade2 (oracle/_ref/ref_erase.inc)
+ *   LogoScan.hpp:1100-1103, 1248-1341, 1421-1461   LogoAnalyzeFrame, AMTEraseLogo::Delogo / CalcFade2 / CalcFade / ReadLogoFrameFile
+ *                                                  (oracle/_ref/ref_erase.inc)
+ *   AMTSource.hpp:291-355   AMTSource::Copy1 / Copy2 / MergeField (oracle/_ref/ref_mergefield.inc)
  * This file adds no arithmetic of its own: every function forwards to the extracted code.
  * `private`/`protected` are opened (oracle build only) so the tests can read the tables the reference
  * keeps private (scales, blackScore, LogoColor sums) -- SURVEY.md Appendix A item 4. */
@@ -202,14 +204,26 @@ struct RefShimAnalyzeClip {
   const LogoAnalyzeFrame* records; int nblocks;
   RefShimPFrame GetFrame(int n, void*) const { return RefShimPFrame(reinterpret_cast<const uint8_t*>(records + (size_t)std::max(0, std::min(nblocks - 1, n)) * 8)); }
 };
+struct RefShimAvsError { std::string msg; };
+struct RefShimEnv {
+  void ThrowError(const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    throw RefShimAvsError{ buf };
+  }
+};
+#include <regex>
 struct RefEraseShim {
   struct { int num_frames; } vi;
   const RefShimAnalyzeClip* analyzeclip;
+  std::vector<int> frameResult;            /* members of AMTEraseLogo the extracted functions use (LogoScan.hpp:1242-1246) */
+  int maxFadeLength;
 #define PVideoFrame RefShimPFrame
 #define IScriptEnvironment2 void
+#define IScriptEnvironment RefShimEnv
 #include "ref_erase.inc"
 #undef PVideoFrame
 #undef IScriptEnvironment2
+#undef IScriptEnvironment
 };
 extern "C" {
 void ref_delogo_u8(uint8_t* dst, int w, int h, int logopitch, int imgpitch, float maxv, const float* A, const float* B, float fade) {
@@ -223,6 +237,56 @@ void ref_calc_fade2(const float* records, int nblocks, int num_frames, int n, fl
   RefShimAnalyzeClip clip{ reinterpret_cast<const LogoAnalyzeFrame*>(records), nblocks };
   RefEraseShim s; s.vi.num_frames = num_frames; s.analyzeclip = &clip;
   s.CalcFade2(n, *fadeT, *fadeB, nullptr);
+}
+/* AMTEraseLogo's fade selection for every frame: ReadLogoFrameFile (when logof_path is given) then CalcFade(n) for n in [0, num_frames).
+ * frame_result (optional, [num_frames]) receives the 0/1/2 state table.  Returns 1, or 0 with the ThrowError text in err. */
+int ref_erase_fades(const float* records, int nblocks, int num_frames, const char* logof_path, int maxFadeLength,
+                    float* out, int* frame_result, char* err, int errlen) {
+  RefShimAnalyzeClip clip{ reinterpret_cast<const LogoAnalyzeFrame*>(records), nblocks };
+  RefEraseShim s; s.vi.num_frames = num_frames; s.analyzeclip = &clip; s.maxFadeLength = maxFadeLength;
+  try {
+    RefShimEnv env;
+    if (logof_path) s.ReadLogoFrameFile(logof_path, &env);
+    for (int n = 0; n < num_frames; ++n) s.CalcFade(n, out[2 * n], out[2 * n + 1], nullptr);
+    if (frame_result && logof_path) memcpy(frame_result, s.frameResult.data(), sizeof(int) * (size_t)num_frames);
+    return 1;
+  } catch (const RefShimAvsError& e) {
+    if (err && errlen > 0) { strncpy(err, e.msg.c_str(), (size_t)errlen - 1); err[errlen - 1] = 0; }
+    return 0;
+  }
+}
+
+} /* extern "C" */
+
+/* ---- AMTSource::Copy1 / Copy2 / MergeField (AMTSource.hpp:291-355), verbatim inside a shim class ---- */
+enum AVPixelFormat { AV_PIX_FMT_YUV420P = 0, AV_PIX_FMT_NV12 = 23 };
+struct AVPixFmtDescriptor { int log2_chroma_w, log2_chroma_h; };
+static const AVPixFmtDescriptor* av_pix_fmt_desc_get(AVPixelFormat) { static const AVPixFmtDescriptor d = { 1, 1 }; return &d; }   /* 4:2:0 */
+struct AVFrame { uint8_t* data[8]; int linesize[8]; int format; };
+struct RefShimWFrameObj   /* PLANAR_Y/U/V come from ref_shim.h */ {
+  uint8_t* p[3]; int pitch[3];
+  uint8_t* GetWritePtr(int pl) { return p[pl == PLANAR_Y ? 0 : pl == PLANAR_U ? 1 : 2]; }
+  int GetPitch(int pl) { return pitch[pl == PLANAR_Y ? 0 : pl == PLANAR_U ? 1 : 2]; }
+};
+struct RefShimWFrame { RefShimWFrameObj o; RefShimWFrameObj* operator->() { return &o; } };
+struct RefSourceShim {
+  struct { int width, height; } vi;
+#define PVideoFrame RefShimWFrame
+#include "ref_mergefield.inc"
+#undef PVideoFrame
+};
+extern "C" {
+/* 8-bit 4:2:0: planar source (nv12 = 0: tU/tV and bU/bV separate planes) or NV12 (nv12 = 1: tU / bU point at the interleaved plane) */
+void ref_merge_field_u8(uint8_t* dY, uint8_t* dU, uint8_t* dV, int dpY, int dpUV,
+                        const uint8_t* tY, const uint8_t* tU, const uint8_t* tV, int tpY, int tpUV,
+                        const uint8_t* bY, const uint8_t* bU, const uint8_t* bV, int bpY, int bpUV, int w, int h, int nv12) {
+  AVFrame top = {}, bottom = {};
+  top.data[0] = (uint8_t*)tY; top.data[1] = (uint8_t*)tU; top.data[2] = (uint8_t*)tV; top.linesize[0] = tpY; top.linesize[1] = top.linesize[2] = tpUV;
+  bottom.data[0] = (uint8_t*)bY; bottom.data[1] = (uint8_t*)bU; bottom.data[2] = (uint8_t*)bV; bottom.linesize[0] = bpY; bottom.linesize[1] = bottom.linesize[2] = bpUV;
+  top.format = bottom.format = nv12 ? AV_PIX_FMT_NV12 : AV_PIX_FMT_YUV420P;
+  RefShimWFrame dst; dst.o.p[0] = dY; dst.o.p[1] = dU; dst.o.p[2] = dV; dst.o.pitch[0] = dpY; dst.o.pitch[1] = dst.o.pitch[2] = dpUV;
+  RefSourceShim s; s.vi.width = w; s.vi.height = h;
+  s.MergeField<uint8_t>(dst, &top, &bottom);
 }
 
 /* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline / parity legs) ---------------------

@@ -49,6 +49,14 @@ public:
   size_t read(MemoryChunk mc) const { if (!mc.length) return 0; return fread(mc.data, 1, mc.length, fp_); }
   template <typename T> T readValue() const { T v; if (read(MemoryChunk((uint8_t*)&v, sizeof(T))) != sizeof(T)) throw IOException(); return v; }
   void seek(int64_t off, int origin) const { if (fseeko(fp_, (off_t)off, origin) != 0) throw IOException(); }
+  /* one text line without its line ending; false at end of file (contract of CoreUtils.hpp:352-375) */
+  bool getline(std::string& line) {
+    line.clear();
+    int c, got = 0;
+    while ((c = fgetc(fp_)) != EOF) { got = 1; if (c == '\n') break; line.push_back((char)c); }
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    return got != 0;
+  }
 };
 
 template <size_t N> static inline void strncpy_s(char (&dst)[N], const char* src, size_t count) {

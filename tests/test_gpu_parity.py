@@ -447,6 +447,13 @@ def test_weave_frames_matches_mergefield(ctx):
     ref = torch.zeros_like(src8)
     ctx.weave_frames(ab.yv12_clip(src8, w, h, n, True), ab.yv12_clip(ref, w, h, n, True), top, bot)
     assert torch.equal(dst, ref)
+    # ... and both equal the reference's OWN MergeField / Copy1 / Copy2 (compiled from AMTSource.hpp:291-355 into oracle/_ref)
+    from oracle import pyoracle as po
+    if po.ref_has_mergefield():
+        g = dst.cpu().numpy()
+        for k in range(n):
+            assert np.array_equal(g[k], po.ref_merge_field(a[top[k]], a[bot[k]], w, h)), ("planar", k)
+            assert np.array_equal(g[k], po.ref_merge_field(nv[top[k]], nv[bot[k]], w, h, nv12=True)), ("nv12", k)
     with pytest.raises(ab.AmtkError, match="index outside"):
         ctx.weave_frames(ab.yv12_clip(src8, w, h, n, True), ab.yv12_clip(dst, w, h, n, True), top, bot + 1)
 

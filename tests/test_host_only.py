@@ -176,6 +176,17 @@ def test_eraselogo_fade_selection(exe, tmp_path):
             exp = po.or_calc_fade2(rec, n, i)
         assert tuple(np.float32(exp)) == tuple(got[i]), i
     assert 0 < direct < n
+    # ... and so does the reference's OWN ReadLogoFrameFile + CalcFade (LogoScan.hpp:1317-1341,1421-1461; compiled from the
+    # reference's lines into oracle/_ref): the product's C++ driver picks the same fades, frame for frame, bit for bit
+    if po.ref_available() and hasattr(po.ref_lib(), "ref_erase_fades"):
+        rf, rstate = po.ref_erase_fades(rec, n, lf, maxfade)
+        assert np.array_equal(rstate, fr)
+        assert np.array_equal(rf.view(np.uint32), got.view(np.uint32))
+        rf0, _ = po.ref_erase_fades(rec, n, None, maxfade)
+        assert np.array_equal(rf0.view(np.uint32), want.view(np.uint32))
+        lf.write_text("%6d S 0 ALL %6d %6d\n%6d S 0 ALL %6d %6d\n" % (22, 20, 26, 58, 55, 61))
+        with pytest.raises(RuntimeError, match="Start and End must be cyclic"):
+            po.ref_erase_fades(rec, n, lf, maxfade)
     # malformed files are rejected with the reference's message
     lf.write_text("%6d S 0 ALL %6d %6d\n%6d S 0 ALL %6d %6d\n" % (22, 20, 26, 58, 55, 61))
     r = run(exe, "fades", lp, lf, rp, n, maxfade, fp, ok=(4,))

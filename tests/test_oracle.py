@@ -191,3 +191,27 @@ def test_port_delogo_and_calcfade2_equal_the_reference_code_live():
             took.add(want[0] == want[1])
         if N >= 23:
             assert took == {True, False}
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_mergefield_is_the_even_odd_row_weave_live():
+    """AMTSource::MergeField / Copy1 / Copy2 compiled from the reference's own lines (AMTSource.hpp:291-355): even rows of
+    every plane from `top`, odd rows from `bottom`, NV12 chroma de-interleaved -- the statement the GPU weave kernel
+    (amtk_weave_frames) is tested against on the device."""
+    if not po.ref_has_mergefield():
+        pytest.skip("prebuilt oracle/_ref predates the MergeField extraction")
+    rng = np.random.default_rng(5)
+    for (w, h) in ((16, 8), (208, 72), (64, 36)):      # heights are multiples of 4: Copy1 writes row pairs of the chroma planes too
+        ysz, cw, ch = w * h, w // 2, h // 2
+        t = rng.integers(0, 256, ysz + 2 * cw * ch).astype(np.uint8)
+        b = rng.integers(0, 256, ysz + 2 * cw * ch).astype(np.uint8)
+        got = po.ref_merge_field(t, b, w, h)
+        for (o, rows, cols) in ((0, h, w), (ysz, ch, cw), (ysz + cw * ch, ch, cw)):
+            exp = t[o:o + rows * cols].reshape(rows, cols).copy()
+            exp[1::2] = b[o:o + rows * cols].reshape(rows, cols)[1::2]
+            assert np.array_equal(got[o:o + rows * cols].reshape(rows, cols), exp)
+
+        def to_nv12(a):
+            uv = np.stack([a[ysz:ysz + cw * ch], a[ysz + cw * ch:]], axis=1).reshape(-1)
+            return np.concatenate([a[:ysz], uv])
+        assert np.array_equal(po.ref_merge_field(to_nv12(t), to_nv12(b), w, h, nv12=True), got)
