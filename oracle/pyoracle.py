@@ -411,6 +411,11 @@ def ref_lib():
             R.ref_merge_field_u8.restype = None
             R.ref_merge_field_u8.argtypes = [c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int, c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int,
                                              c_u8_p, c_u8_p, c_u8_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        if hasattr(R, "ref_analyze_getframe"):                  # round 2: AMTAnalyzeLogo::GetFrameT / LogoFrame::ScanFrame themselves
+            R.ref_analyze_getframe.restype = None
+            R.ref_analyze_getframe.argtypes = [V, V, V, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p]
+            R.ref_scan_frame.restype = None
+            R.ref_scan_frame.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]
         if hasattr(R, "ref_erase_fades"):
             R.ref_erase_fades.restype = C.c_int
             R.ref_erase_fades.argtypes = [c_float_p, C.c_int, C.c_int, C.c_char_p, C.c_int, c_float_p, c_i32_p, C.c_char_p, C.c_int]
@@ -479,6 +484,32 @@ def ref_erase_fades(records, num_frames, logof_path=None, max_fade_length=16):
     if not ok:
         raise RuntimeError(err.value.decode("utf-8", "replace"))
     return out, (fr if logof_path else None)
+
+
+def ref_has_drivers():
+    return ref_available() and hasattr(ref_lib(), "ref_analyze_getframe")
+
+
+def ref_analyze_getframe(dl, ft, fb, frames, w, h, n, bits=8):
+    """The reference's own AMTAnalyzeLogo::GetFrameT (LogoScan.hpp:1119-1161) for analyze frame n: the 8 LogoAnalyzeFrame
+    records (8, 33) of source frames 8n..8n+7 (clamped to the last one, :1133).  frames: (N, w*h*3/2) packed planar 4:2:0."""
+    fr = np.ascontiguousarray(frames)
+    d = dl.dims()
+    out = np.zeros((8, 33), np.float32)
+    ref_lib().ref_analyze_getframe(dl.ptr, ft.ptr, fb.ptr, d["imgx"], d["imgy"], fr.ctypes.data, fr.shape[0], w, h, bits, int(n), _p(out, c_float_p))
+    return out
+
+
+def ref_scan_frame_code(logos, frame, w, h, bits=8):
+    """The reference's own LogoFrame::ScanFrame (LogoScan.hpp:1543-1568) on one packed frame; logos: deint RefLogo objects
+    or None (an invalid logo -> corr0 = 0, corr1 = -1).  Returns (len(logos), 2) float32."""
+    fr = np.ascontiguousarray(frame)
+    arr = (C.c_void_p * len(logos))(*[(lg.ptr if lg is not None else None) for lg in logos])
+    big = max([lg.dims()["w"] * lg.dims()["h"] for lg in logos if lg is not None] + [1])
+    mem_d, mem_w = np.zeros(big + 8, np.float32), np.zeros(big + 8, np.float32)
+    out = np.zeros((len(logos), 2), np.float32)
+    ref_lib().ref_scan_frame(arr, len(logos), fr.ctypes.data, w, h, bits, _p(mem_d, c_float_p), _p(mem_w, c_float_p), _p(out, c_float_p))
+    return out
 
 
 def ref_has_mergefield():

@@ -9,6 +9,7 @@
  *   LogoScan.hpp:1100-1103, 1248-1341, 1421-1461   LogoAnalyzeFrame, AMTEraseLogo::Delogo / CalcFade2 / CalcFade / ReadLogoFrameFile
  *                                                  (oracle/_ref/ref_erase.inc)
  *   AMTSource.hpp:291-355   AMTSource::Copy1 / Copy2 / MergeField (oracle/_ref/ref_mergefield.inc)
+ *   LogoScan.hpp:1119-1161, 1543-1568   AMTAnalyzeLogo::GetFrameT, LogoFrame::ScanFrame (ref_analyze.inc, ref_scanframe.inc)
  * This file adds no arithmetic of its own: every function forwards to the extracted code.
  * `private`/`protected` are opened (oracle build only) so the tests can read the tables the reference
  * keeps private (scales, blackScore, LogoColor sums) -- SURVEY.md Appendix A item 4. */
@@ -287,6 +288,78 @@ void ref_merge_field_u8(uint8_t* dY, uint8_t* dU, uint8_t* dV, int dpY, int dpUV
   RefShimWFrame dst; dst.o.p[0] = dY; dst.o.p[1] = dU; dst.o.p[2] = dV; dst.o.pitch[0] = dpY; dst.o.pitch[1] = dst.o.pitch[2] = dpUV;
   RefSourceShim s; s.vi.width = w; s.vi.height = h;
   s.MergeField<uint8_t>(dst, &top, &bottom);
+}
+
+} /* extern "C" */
+
+/* ---- AMTAnalyzeLogo::GetFrameT (LogoScan.hpp:1119-1161) and LogoFrame::ScanFrame (:1543-1568), verbatim inside shim classes.
+ * The stand-ins supply exactly the members the two functions touch: a frame with GetReadPtr/GetPitch/GetWritePtr, a child clip
+ * handing out packed planar frames, NewVideoFrame returning the caller's output block, VideoInfo with the fields read. */
+struct RefShimVideoInfo { int width, height, num_frames, bits; int BitsPerComponent() const { return bits; } };
+struct RefShimRFrameObj {
+  const uint8_t* p[3]; int pitch[3]; uint8_t* w;
+  const uint8_t* GetReadPtr(int pl = PLANAR_Y) const { return p[pl == PLANAR_Y ? 0 : pl == PLANAR_U ? 1 : 2]; }
+  int GetPitch(int pl = PLANAR_Y) const { return pitch[pl == PLANAR_Y ? 0 : pl == PLANAR_U ? 1 : 2]; }
+  uint8_t* GetWritePtr() { return w; }
+};
+struct RefShimRFrame { RefShimRFrameObj o; RefShimRFrameObj* operator->() { return &o; } };
+struct RefShimChild {                       /* packed planar 4:2:0 frames, tight pitches, bytes per sample bps */
+  const uint8_t* base; long long frame_stride; int w, h, bps;
+  RefShimRFrame GetFrame(int n, void*) const {
+    RefShimRFrame f; const uint8_t* fr = base + (long long)n * frame_stride;
+    f.o.p[0] = fr; f.o.p[1] = fr + (size_t)w * h * bps; f.o.p[2] = f.o.p[1] + (size_t)(w / 2) * (h / 2) * bps;
+    f.o.pitch[0] = w * bps; f.o.pitch[1] = f.o.pitch[2] = (w / 2) * bps; f.o.w = nullptr;
+    return f;
+  }
+};
+struct RefShimEnv2 {
+  uint8_t* out;
+  RefShimRFrame NewVideoFrame(const RefShimVideoInfo&) { RefShimRFrame f; f.o.p[0] = f.o.p[1] = f.o.p[2] = nullptr; f.o.pitch[0] = f.o.pitch[1] = f.o.pitch[2] = 256; f.o.w = out; return f; }
+};
+struct RefAnalyzeShim {
+  RefShimVideoInfo vi, srcvi;
+  const RefShimChild* child;
+  std::unique_ptr<LogoDataParam> deintLogo, fieldLogoT, fieldLogoB;       /* borrowed: released again before destruction */
+  LogoHeader header;
+#define PVideoFrame RefShimRFrame
+#define IScriptEnvironment2 RefShimEnv2
+#include "ref_analyze.inc"
+#undef PVideoFrame
+#undef IScriptEnvironment2
+};
+struct RefDeintArr { LogoDataParam** p; LogoDataParam& operator[](int i) { return *p[i]; } };
+struct RefScanShim {
+  int numLogos; RefShimVideoInfo vi; RefDeintArr deintArr;
+  struct EvalResult { float corr0, corr1; };
+#define PVideoFrame RefShimRFrame
+#include "ref_scanframe.inc"
+#undef PVideoFrame
+};
+extern "C" {
+/* out: [8][33] floats = the 8 LogoAnalyzeFrame records of analyze frame n (LogoScan.hpp:1128-1157) */
+void ref_analyze_getframe(void* deint, void* top, void* bottom, int imgx, int imgy, const void* frames, int num_frames, int w, int h,
+                          int bits, int n, float* out) {
+  RefShimChild child{ (const uint8_t*)frames, (long long)w * h * 3 / 2 * (bits > 8 ? 2 : 1), w, h, bits > 8 ? 2 : 1 };
+  RefAnalyzeShim s;
+  s.child = &child; s.srcvi = RefShimVideoInfo{ w, h, num_frames, bits }; s.vi = s.srcvi;
+  s.deintLogo.reset((LogoDataParam*)deint); s.fieldLogoT.reset((LogoDataParam*)top); s.fieldLogoB.reset((LogoDataParam*)bottom);
+  LogoDataParam* d = (LogoDataParam*)deint;
+  s.header = LogoHeader(d->getWidth(), d->getHeight(), d->getLogUVx(), d->getLogUVy(), w, h, imgx, imgy, "");
+  RefShimEnv2 env{ (uint8_t*)out };
+  if (bits > 8) s.GetFrameT<uint16_t>(n, &env); else s.GetFrameT<uint8_t>(n, &env);
+  s.deintLogo.release(); s.fieldLogoT.release(); s.fieldLogoB.release();
+}
+/* out: [numLogos][2]; logos[i] may be NULL (an invalid logo, LogoScan.hpp:1551-1558).  pitch_y as the reference passes it (BYTES, :1547) */
+void ref_scan_frame(void** logos, int numLogos, const void* frame, int w, int h, int bits, float* memDeint, float* memWork, float* out) {
+  static LogoDataParam invalid;
+  std::vector<LogoDataParam*> arr(numLogos);
+  for (int i = 0; i < numLogos; ++i) arr[i] = logos[i] ? (LogoDataParam*)logos[i] : &invalid;
+  RefShimChild child{ (const uint8_t*)frame, 0, w, h, bits > 8 ? 2 : 1 };
+  RefShimRFrame f = child.GetFrame(0, nullptr);
+  RefScanShim s; s.numLogos = numLogos; s.vi = RefShimVideoInfo{ w, h, 1, bits }; s.deintArr = RefDeintArr{ arr.data() };
+  float maxv = (float)((1 << bits) - 1);
+  if (bits > 8) s.ScanFrame<uint16_t>(f, memDeint, memWork, maxv, reinterpret_cast<RefScanShim::EvalResult*>(out));
+  else s.ScanFrame<uint8_t>(f, memDeint, memWork, maxv, reinterpret_cast<RefScanShim::EvalResult*>(out));
 }
 
 /* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline / parity legs) ---------------------

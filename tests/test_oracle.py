@@ -215,3 +215,28 @@ def test_reference_mergefield_is_the_even_odd_row_weave_live():
             uv = np.stack([a[ysz:ysz + cw * ch], a[ysz + cw * ch:]], axis=1).reshape(-1)
             return np.concatenate([a[:ysz], uv])
         assert np.array_equal(po.ref_merge_field(to_nv12(t), to_nv12(b), w, h, nv12=True), got)
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_frame_drivers_equal_their_restated_compositions_live():
+    """AMTAnalyzeLogo::GetFrameT (LogoScan.hpp:1119-1161) and LogoFrame::ScanFrame (:1543-1568) compiled from the reference's
+    own lines: the compositions the parity tests use (ref_analyze_frame / ref_scan_frame: the reference's DeintY, CopyY and
+    EvaluateLogo called in the order those functions call them) give the same bits, including the source-frame clamp at the
+    clip end (:1133), the |.| of every evaluation, and the (0, -1) result for invalid or wrong-sized logos (:1551-1558)."""
+    if not po.ref_has_drivers():
+        pytest.skip("prebuilt oracle/_ref predates the GetFrameT/ScanFrame extraction")
+    w, h, imgx, imgy, N = 256, 128, 160, 32, 13
+    lg = synth.make_logo(64, 64)
+    fr = synth.make_frames(40, N, w, h, device="cpu", logo=lg, imgx=imgx, imgy=imgy, logo_period=12).numpy()
+    raw = po.RefLogo.create(lg["data"], 64, 64, w, h, imgx, imgy)
+    de, top, bot = raw.deint().create_mask(0.35), raw.field(0).create_mask(0.35), raw.field(1).create_mask(0.35)
+    Y = fr[:, : w * h].reshape(N, h, w)
+    for n in range((N + 7) // 8):
+        got = po.ref_analyze_getframe(de, top, bot, fr, w, h, n)
+        want = np.stack([po.ref_analyze_frame(de, top, bot, Y[min(N - 1, 8 * n + i)]) for i in range(8)])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), n
+    other = po.RefLogo.create(lg["data"], 64, 64, w + 16, h, imgx, imgy).deint().create_mask(0.35)      # made for another frame size
+    for k in (0, 5, N - 1):
+        got = po.ref_scan_frame_code([de, None, other], fr[k], w, h)
+        assert np.array_equal(got[0].view(np.uint32), po.ref_scan_frame(de, Y[k]).view(np.uint32))
+        assert tuple(got[1]) == (0.0, -1.0) and tuple(got[2]) == (0.0, -1.0)
