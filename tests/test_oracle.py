@@ -240,3 +240,54 @@ def test_reference_frame_drivers_equal_their_restated_compositions_live():
         got = po.ref_scan_frame_code([de, None, other], fr[k], w, h)
         assert np.array_equal(got[0].view(np.uint32), po.ref_scan_frame(de, Y[k]).view(np.uint32))
         assert tuple(got[1]) == (0.0, -1.0) and tuple(got[2]) == (0.0, -1.0)
+
+
+def test_erase_and_weave_golden_from_the_reference_code(tmp_path):
+    """Committed golden vectors produced by the reference's own Delogo / CalcFade2 / CalcFade + ReadLogoFrameFile / MergeField
+    (tests/golden/gen_golden.py, round 2): the C port, the product's host-side amtk_calc_fade2 and the even/odd-row weave
+    statement reproduce them -- also where /root/reference is absent."""
+    import amatsukaze_b200 as ab
+    g = GOLD["erase"]
+    rng = np.random.default_rng(g["seed"])
+    it = iter(g["delogo"])
+    for dtype, maxv in (("uint8", 255.0), ("uint16", 1023.0)):
+        for (w, h, lp, ip) in ((64, 64, 64, 96), (32, 16, 64, 200)):
+            img = rng.integers(0, int(maxv) + 1, size=(h, ip)).astype(dtype)
+            A = rng.uniform(0.8, 1.6, size=h * lp).astype(np.float32)
+            B = rng.uniform(-0.6, 0.1, size=h * lp).astype(np.float32)
+            for fade in (0.1, 0.5, 1.0):
+                e = next(it)
+                assert (e["dtype"], e["w"], e["h"], e["fade"]) == (dtype, w, h, fade)
+                a = img.copy()
+                po.or_delogo(a, A, B, fade, maxv, logopitch=lp, imgpitch=ip, w=w, h=h)
+                assert digest(a) == e["sha"], e
+    c2 = g["calc_fade2"]
+    N = c2["n"]
+    rng = np.random.default_rng(c2["seed"])
+    rec = rng.uniform(0.0, 1.0, size=(N, 33)).astype(np.float32)
+    for k in range(N):
+        rec[k, :11] += np.abs(np.arange(11) - (0 if (k // 7) % 2 == 0 else 10)) * np.float32(0.5)
+    want = np.array(c2["fades_bits"], np.uint32).view(np.float32).reshape(N, 2)
+    assert bits(np.array([po.or_calc_fade2(rec, N, n) for n in range(N)], np.float32)) == c2["fades_bits"]
+    assert bits(np.array([ab.calc_fade2(rec, N, n) for n in range(N)], np.float32)) == c2["fades_bits"]        # product (host code, no GPU)
+    # CalcFade with a logoframe file: uniform +-maxfade/2 neighbourhoods take 0 / 1, the rest CalcFade2 (LogoScan.hpp:1317-1341)
+    cf = g["calc_fade"]
+    state = np.array(cf["state"], np.int32)
+    half = cf["maxfade"] >> 1
+    exp = np.zeros((N, 2), np.float32)
+    for i in range(N):
+        win = state[np.clip(np.arange(i - half, i + half + 1), 0, N - 1)]
+        exp[i] = ((1.0, 1.0) if state[i] == 2 else (0.0, 0.0)) if np.all(win == win[0]) else want[i]
+    assert bits(exp) == cf["fades_bits"]
+    assert set(state.tolist()) == {0, 1, 2}
+    # MergeField: even rows from top, odd rows from bottom, every plane
+    m = GOLD["mergefield"]
+    w, h = m["w"], m["h"]
+    rng = np.random.default_rng(m["seed"])
+    msz = w * h * 3 // 2
+    t = rng.integers(0, 256, msz).astype(np.uint8)
+    b = rng.integers(0, 256, msz).astype(np.uint8)
+    out = t.copy()
+    for (o, rows, cols) in ((0, h, w), (w * h, h // 2, w // 2), (w * h + (w // 2) * (h // 2), h // 2, w // 2)):
+        out[o:o + rows * cols].reshape(rows, cols)[1::2] = b[o:o + rows * cols].reshape(rows, cols)[1::2]
+    assert digest(out) == m["sha"]
