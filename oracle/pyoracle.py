@@ -416,6 +416,11 @@ def ref_lib():
             R.ref_analyze_getframe.argtypes = [V, V, V, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p]
             R.ref_scan_frame.restype = None
             R.ref_scan_frame.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]
+        if hasattr(R, "ref_read_timecode"):                     # round 2: FilteredSource.hpp side-file readers
+            R.ref_read_timecode.restype = C.c_int
+            R.ref_read_timecode.argtypes = [C.c_char_p, c_f64_p, C.c_int, C.POINTER(C.c_int)]
+            R.ref_decimate_map.restype = C.c_int
+            R.ref_decimate_map.argtypes = [C.c_char_p, C.c_int, c_i32_p, C.c_int, C.c_char_p, C.c_int]
         if hasattr(R, "ref_erase_fades"):
             R.ref_erase_fades.restype = C.c_int
             R.ref_erase_fades.argtypes = [c_float_p, C.c_int, C.c_int, C.c_char_p, C.c_int, c_float_p, c_i32_p, C.c_char_p, C.c_int]
@@ -510,6 +515,32 @@ def ref_scan_frame_code(logos, frame, w, h, bits=8):
     out = np.zeros((len(logos), 2), np.float32)
     ref_lib().ref_scan_frame(arr, len(logos), fr.ctypes.data, w, h, bits, _p(mem_d, c_float_p), _p(mem_w, c_float_p), _p(out, c_float_p))
     return out
+
+
+def ref_has_sidefiles():
+    return ref_available() and hasattr(ref_lib(), "ref_read_timecode")
+
+
+def ref_read_timecode(path):
+    """The reference's own AMTFilterSource::readTimecodeFile + base-fps estimate (FilteredSource.hpp:163-188,197-210).
+    Returns (timeCodes list, vfrTimingFps) or None when the file cannot be opened."""
+    out = np.zeros(1 << 16, np.float64)
+    fps = C.c_int(0)
+    n = ref_lib().ref_read_timecode(str(path).encode(), _p(out, c_f64_p), out.size, C.byref(fps))
+    return None if n < 0 else (out[:n].tolist(), fps.value)
+
+
+def ref_decimate_map(duration_path, num_source_frames):
+    """The reference's own AMTDecimate (FilteredSource.hpp:645-660,663-666): source frame of every output frame.  Raises
+    RuntimeError with the ThrowError text on a frame-count mismatch, IOError when the file cannot be opened."""
+    m = np.zeros(1 << 16, np.int32)
+    err = C.create_string_buffer(512)
+    n = ref_lib().ref_decimate_map(str(duration_path).encode(), int(num_source_frames), _p(m, c_i32_p), m.size, err, 512)
+    if n == -1:
+        raise IOError("cannot open " + str(duration_path))
+    if n == -2:
+        raise RuntimeError(err.value.decode("utf-8", "replace"))
+    return m[:n].tolist()
 
 
 def ref_has_mergefield():

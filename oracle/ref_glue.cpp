@@ -10,6 +10,7 @@
  *                                                  (oracle/_ref/ref_erase.inc)
  *   AMTSource.hpp:291-355   AMTSource::Copy1 / Copy2 / MergeField (oracle/_ref/ref_mergefield.inc)
  *   LogoScan.hpp:1119-1161, 1543-1568   AMTAnalyzeLogo::GetFrameT, LogoFrame::ScanFrame (ref_analyze.inc, ref_scanframe.inc)
+ *   FilteredSource.hpp:163-188,197-210,645-660,663-666   readTimecodeFile + base-fps estimate, AMTDecimate ctor body + GetFrame
  * This file adds no arithmetic of its own: every function forwards to the extracted code.
  * `private`/`protected` are opened (oracle build only) so the tests can read the tables the reference
  * keeps private (scales, blackScore, LogoColor sums) -- SURVEY.md Appendix A item 4. */
@@ -360,6 +361,61 @@ void ref_scan_frame(void** logos, int numLogos, const void* frame, int w, int h,
   float maxv = (float)((1 << bits) - 1);
   if (bits > 8) s.ScanFrame<uint16_t>(f, memDeint, memWork, maxv, reinterpret_cast<RefScanShim::EvalResult*>(out));
   else s.ScanFrame<uint8_t>(f, memDeint, memWork, maxv, reinterpret_cast<RefScanShim::EvalResult*>(out));
+}
+
+} /* extern "C" */
+
+/* ---- FilteredSource.hpp: readTimecodeFile (:163-188) + the base-fps estimate (:197-210), AMTDecimate ctor body (:645-660) + GetFrame
+ * (:663-666), verbatim inside shim classes ---- */
+#include <numeric>
+static inline const std::string& to_tstring(const std::string& s) { return s; }
+struct RefTimecodeShim {
+  std::vector<double> timeCodes_;
+  int vfrTimingFps_ = 0;
+#include "ref_timecode.inc"
+  void estimateFps() {
+#include "ref_timecode_fps.inc"
+  }
+};
+struct RefDecimateChild { int GetFrame(int n, void*) { return n; } };
+struct RefDecimateShim {
+  std::vector<int> durations, framesMap;
+  struct { int num_frames; } vi;
+  RefDecimateChild childobj, *child = &childobj;
+  void construct(const std::string& duration, RefShimEnv* env) {
+#include "ref_decimate_ctor.inc"
+  }
+#define PVideoFrame int
+#define __stdcall
+#define IScriptEnvironment RefShimEnv
+#include "ref_decimate_getframe.inc"
+#undef PVideoFrame
+#undef __stdcall
+#undef IScriptEnvironment
+};
+extern "C" {
+/* returns the number of time codes (incl. the total), -1 when the file cannot be opened; *fps = vfrTimingFps (0 = no grid fits better) */
+int ref_read_timecode(const char* path, double* out, int cap, int* fps) {
+  try {
+    RefTimecodeShim s; s.readTimecodeFile(path);
+    if (!s.timeCodes_.empty()) s.estimateFps();
+    int n = (int)s.timeCodes_.size();
+    for (int i = 0; i < n && i < cap; ++i) out[i] = s.timeCodes_[i];
+    *fps = s.vfrTimingFps_;
+    return n;
+  } catch (const IOException&) { return -1; }
+}
+/* AMTDecimate on a source of num_source_frames: writes the source frame of every output frame; returns the output frame count,
+ * -1 unreadable file, -2 with the ThrowError text in err */
+int ref_decimate_map(const char* duration_path, int num_source_frames, int* map, int cap, char* err, int errlen) {
+  try {
+    RefDecimateShim s; s.vi.num_frames = num_source_frames;
+    RefShimEnv env;
+    s.construct(duration_path, &env);
+    for (int i = 0; i < s.vi.num_frames && i < cap; ++i) map[i] = s.GetFrame(i, &env);
+    return s.vi.num_frames;
+  } catch (const IOException&) { return -1; }
+  catch (const RefShimAvsError& e) { if (err && errlen > 0) { strncpy(err, e.msg.c_str(), (size_t)errlen - 1); err[errlen - 1] = 0; } return -2; }
 }
 
 /* ---- CPU baseline loop for bench.py (--impl reference and the cpu_baseline / parity legs) ---------------------

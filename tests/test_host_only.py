@@ -99,6 +99,44 @@ def test_decimate_map_and_mismatch(exe, tmp_path):
     assert "failed to open" in r.stdout
 
 
+def test_sidefile_readers_equal_the_reference_code(exe, tmp_path):
+    """The product's TimecodeFile and AMTDecimate (host/filters.hpp) against the reference's OWN readTimecodeFile + base-fps
+    estimate and AMTDecimate constructor/GetFrame, compiled from FilteredSource.hpp:163-188,197-210,645-660,663-666 into
+    oracle/_ref: same time codes (compared at the driver's printed 1e-6 ms resolution), same vfrTimingFps, same frame map, same
+    mismatch message; edge cases: empty file, one stamp, total line with trailing text, CRLF, comments, no total line."""
+    if not (po.ref_available() and po.ref_has_sidefiles()):
+        pytest.skip("oracle/_ref (with the side-file readers) not built: needs /root/reference")
+    rng = np.random.default_rng(3)
+    cases = []
+    for grid in (60, 120, 240, 0):
+        t, stamps = 0.0, []
+        for _ in range(int(rng.integers(2, 90))):
+            stamps.append(int(round(t)))
+            t += (1001.0 / grid * 1000.0 / 1000.0 * int(rng.integers(1, 4)) * (1000.0 / 1000.0)) if grid else float(rng.integers(5, 80))
+        body = "# timecode format v2\n" + "".join("%d\n" % v for v in stamps)
+        cases += [body + "# total: %.3f\n" % (t / 1000.0), body, body + "\r\n#comment\n\n"]
+    cases += ["", "17\n", "# total: 12.5\n", "5\n9\n# total: 1.0 trailing\n33\n"]
+    for k, text in enumerate(cases):
+        p = tmp_path / ("tc%d.txt" % k)
+        p.write_bytes(text.encode())
+        out = run(exe, "timecode", p).stdout.split()
+        codes, fps = po.ref_read_timecode(p)
+        assert out[0] == "ok=1" and out[1] == "n=%d" % len(codes) and out[2] == "fps=%d" % fps, (k, out[:3], len(codes), fps)
+        assert [float(x) for x in out[3:]] == [float("%.6f" % c) for c in codes], k
+    assert po.ref_read_timecode(tmp_path / "missing.txt") is None and "ok=0" in run(exe, "timecode", tmp_path / "missing.txt").stdout
+    for k in range(8):
+        dur = [int(v) for v in rng.integers(1, 4, size=int(rng.integers(1, 60)))]
+        d = tmp_path / ("dur%d.txt" % k)
+        d.write_text("".join("%d\n" % v for v in dur))
+        want = po.ref_decimate_map(d, sum(dur))
+        out = run(exe, "decimate", d, sum(dur)).stdout
+        assert out.split("map:")[0].strip() == "frames=%d" % len(want) and [int(x) for x in out.split("map:")[1].split()] == want
+        with pytest.raises(RuntimeError) as ei:
+            po.ref_decimate_map(d, sum(dur) + 1)
+        r = run(exe, "decimate", d, sum(dur) + 1, ok=(4,))
+        assert "[AMTDecimate] # of frames does not match." in str(ei.value) and str(ei.value).split("]")[1].strip().split("(")[0] in r.stdout
+
+
 def test_telecine_side_files_from_counts(exe, tmp_path):
     n = 43
     counts = np.zeros((n, 12), np.int32)
